@@ -1,0 +1,1030 @@
+// Fused SGNN policy/value forward(+backward) kernel: one CTA walks one rollout graph at a time and keeps
+// the whole graph on chip (node embeddings, exp-transformed edge-MLP pre-activations, CSR adjacency).
+//
+// Reference dataflow replaced (all fp32):
+//   urban_planning/models/state_encoder.py:184-214  encoder (node Linear, 2x {gather -> edge MLP -> scatter},
+//                                                    masked means, 1-query attention, numeric MLP)
+//   urban_planning/models/policy.py:45-104           masked categorical heads (log-prob, entropy, argmax)
+//   urban_planning/models/value.py:36-39             value head
+//   khrylib/rl/agents/agent_pg.py:19-23 + urban_planning/agents/urban_planning_agent.py:363-371   losses
+//   autograd of all of the above (urban_planning_agent.py:335), hand-derived
+//
+// Algebra used (exact in real arithmetic):
+//   * W_l [h_u | h_v] = P_u + Q_v with node-level P = h W_l[:, :16]^T + b, Q = h W_l[:, 16:]^T;
+//   * tanh(P_u + Q_v) = 1 - 2 / (exp(2 P_u) exp(2 Q_v) + 1): exp(2P), exp(2Q) are taken once per NODE, an edge
+//     costs one FMA + one MUFU.RCP per channel and direction;  he = (t1 + t2)/2 = 1 - r1 - r2;
+//   * he is symmetric in (u, v), so the scatter-add becomes an atomics-free PULL over a symmetrised CSR;
+//   * attention with one query: softmax_i(q'.k'_i/4) only needs (Kc^T q').h_i, and sum_i a_i v'_i = Vc hbar + vbc;
+//   * land-use head first layer on [he | hc | he*hc | he-hc] = Weff he + ceff with a per-graph 32x16 Weff;
+//   * only mask-true candidates need the head: masked logits are exactly 0-probability.
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+#include "blob.h"
+#include "layout.h"
+
+namespace upb {
+
+constexpr int NT = 512;          // threads per CTA
+constexpr int NW = NT / 32;      // warps per CTA
+constexpr int NS = 464;          // nodes kept in shared memory
+constexpr int AS = 5120;         // directed adjacency entries kept in shared memory
+constexpr int KS = 256;          // action candidates kept in shared memory
+constexpr int CH = 64;           // candidate chunk of the head backward
+constexpr float MASK_FILL = -4294967296.0f;   // float32(-2**32 + 1), policy.py:50
+constexpr float EPS_DEG = 1e-6f;               // state_encoder.py:11
+
+// ---- shared memory map (floats) -----------------------------------------------------------------------
+// weights (per CTA, loaded once per launch)
+constexpr int S_WET = 0;                   // [24][16]  enc_w^T (row 23 zero)
+constexpr int S_BE = S_WET + 384;          // [16]
+constexpr int S_WPQ0 = S_BE + 16;          // [32][16]  rows 0-15: gcn_w[o][0:16] (P), rows 16-31: gcn_w[o-16][16:32] (Q)
+constexpr int S_B0 = S_WPQ0 + 512;         // [16]
+constexpr int S_WPQ1 = S_B0 + 16;
+constexpr int S_B1 = S_WPQ1 + 512;
+constexpr int S_QC = S_B1 + 16;            // [16][16]  Win_q Wq
+constexpr int S_QBC = S_QC + 256;          // [16]      Win_q bq + bin_q
+constexpr int S_KC = S_QBC + 16;           // [16][16]  Win_k Wk
+constexpr int S_VC = S_KC + 256;           // [16][16]  Win_v Wv
+constexpr int S_VBC = S_VC + 256;          // [16]
+constexpr int S_WO = S_VBC + 16;           // [16][16]
+constexpr int S_BO = S_WO + 256;           // [16]
+constexpr int S_LUW0 = S_BO + 16;          // [32][64]
+constexpr int S_LUB0 = S_LUW0 + 2048;      // [32]
+constexpr int S_LUW1 = S_LUB0 + 32;        // [32]
+constexpr int S_RDW0 = S_LUW1 + 32;        // [32][16]
+constexpr int S_RDW0T = S_RDW0 + 512;      // [16][32]
+constexpr int S_RDB0 = S_RDW0T + 512;      // [32]
+constexpr int S_RDW1 = S_RDB0 + 32;        // [32]
+constexpr int S_WEND = S_RDW1 + 32;
+
+// per-graph small vectors
+constexpr int V_X52 = 0;        // [52] numerical features (padded to 56)
+constexpr int V_XCUR = 56;      // [24]
+constexpr int V_HC = 80;        // [16]
+constexpr int V_A0 = 96;        // [64] numeric hidden
+constexpr int V_SV = 160;       // [67] value features: hnum | mean_h | mean_he | att | stage (padded to 68)
+constexpr int V_QP = 228;       // [16] q'
+constexpr int V_QK = 244;       // [16] Kc^T q' / 4
+constexpr int V_HBAR = 260;     // [16]
+constexpr int V_VP = 276;       // [16] v' = Vc hbar + vbc
+constexpr int V_Y0 = 292;       // [32]
+constexpr int V_Y1 = 324;       // [32]
+constexpr int V_WEFFT = 356;    // [16][32] Weff^T (land use)
+constexpr int V_CEFF = 868;     // [32]
+constexpr int V_GSV = 900;      // [68]
+constexpr int V_D0 = 968;       // [32]
+constexpr int V_D1 = 1000;      // [32]
+constexpr int V_DN0 = 1032;     // [64]
+constexpr int V_DN1 = 1096;     // [16]
+constexpr int V_GVP = 1112;     // [16]
+constexpr int V_GHBAR = 1128;   // [16]
+constexpr int V_GSH = 1144;     // [16]
+constexpr int V_GQP = 1160;     // [16]
+constexpr int V_GHC = 1176;     // [16]
+constexpr int V_CE = 1192;      // [16] g_mean_he / e
+constexpr int V_GMN = 1208;     // [16] g_mean_h / n
+constexpr int V_GWEFF = 1224;   // [32][16]
+constexpr int V_GC = 1736;      // [32]
+constexpr int V_GW2 = 1768;     // [32]
+constexpr int V_TMP16 = 1800;   // [16] block-reduce results
+constexpr int V_TMP16B = 1816;  // [16]
+constexpr int V_SC = 1832;      // [24] scalars
+constexpr int V_END = 1856;
+// scalar slots
+constexpr int SC_VALUE = 0, SC_MAX = 1, SC_SUM = 2, SC_LSE = 3, SC_ENT = 4, SC_LOGP = 5, SC_GV = 6, SC_GLP = 7,
+              SC_GH = 8, SC_Z = 9, SC_SLOT = 10, SC_BEST = 11, SC_GDOT = 12;
+
+constexpr int S_VEC = S_WEND;
+constexpr int S_RED = S_VEC + V_END;             // [NW][20] block-reduce scratch
+constexpr int S_INV = S_RED + NW * 20;           // [NS]
+constexpr int S_ALPHA = S_INV + NS;              // [NS]
+constexpr int S_Z = S_ALPHA + NS;                // [KS]
+constexpr int S_GZ = S_Z + KS;                   // [KS]
+constexpr int S_GHEAD = S_GZ + KS;               // [KS][16]
+constexpr int S_CUV = S_GHEAD + KS * 16;         // [KS] u32
+constexpr int S_CIDX = S_CUV + KS;               // [KS] i32
+constexpr int S_RP = S_CIDX + KS;                // [(NS+8)/2] u16 pairs
+constexpr int S_ADJ = S_RP + (NS + 8) / 2;       // [AS] u32
+constexpr int S_EPQ = S_ADJ + AS;                // [NS][32]
+constexpr int S_GPQ = S_EPQ + NS * 32;           // [NS][32]   (aliased by the head-backward chunk buffers)
+constexpr int S_H = S_GPQ + NS * 32;             // [NS][16]
+constexpr int S_TOTAL = S_H + NS * 16;
+constexpr size_t SMEM_BYTES = (size_t)S_TOTAL * 4;
+static_assert(SMEM_BYTES <= 232448, "shared memory budget (227 KB)");
+static_assert(NW * 512 <= NS * 32, "cross-warp reduction buffer aliases the EPQ region");
+static_assert(CH * (32 + 32 + 16) <= NS * 32, "chunk buffers alias the GPQ region");
+
+// per-CTA global scratch (floats): saved layer inputs + big-graph arrays
+__host__ __device__ inline size_t scratch_floats(int n_cap, int e_cap) {
+  const size_t kcap = (size_t)(e_cap > n_cap ? e_cap : n_cap);
+  return (size_t)n_cap * (16 + 16 + 32 + 32 + 16 + 2) + kcap * 18 + 64;
+}
+
+struct StepArgs {
+  const uint8_t* blob;
+  const int* ids;
+  int count;
+  const float* params;
+  const float* actions;
+  const float* adv;
+  const float* ret;
+  const float* fixed_lp;
+  const float* exps;
+  float inv_batch, inv_ind;
+  float clip_eps, c_value, c_entropy;
+  float* out_value;
+  float* out_logp;
+  float* out_entropy;
+  int* out_greedy;
+  float* gpart;        // [gridDim.x][G_ROW]
+  float* scratch;      // [gridDim.x][scratch_stride]
+  size_t scratch_stride;
+  int n_cap, e_cap;
+};
+
+// ---- small device helpers ------------------------------------------------------------------------------
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// exp(2a) with 2a clamped to +-80 so products of two factors stay finite and non-zero
+__device__ __forceinline__ float exp2a(float a) {
+  const float t = fminf(fmaxf(a * 2.8853900817779268f, -115.41560327111707f), 115.41560327111707f);
+  return ex2_approx(t);
+}
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ float4 f4(float a) { return make_float4(a, a, a, a); }
+__device__ __forceinline__ float4 operator+(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__device__ __forceinline__ float4 operator*(float4 a, float s) { return make_float4(a.x * s, a.y * s, a.z * s, a.w * s); }
+__device__ __forceinline__ float4 operator*(float4 a, float4 b) { return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w); }
+__device__ __forceinline__ float dot4(float4 a, float4 b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
+__device__ __forceinline__ float comp(const float4& v, int j) { return j == 0 ? v.x : j == 1 ? v.y : j == 2 ? v.z : v.w; }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Deterministic block reductions.  `red` is NW*20 floats of scratch; results land in out[] (shared).
+// All threads must call; two __syncthreads inside.
+__device__ __forceinline__ float block_sum1(float v, float* red) {
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float s = 0.f;
+#pragma unroll
+  for (int w = 0; w < NW; ++w) s += red[w];
+  __syncthreads();
+  return s;
+}
+__device__ __forceinline__ float block_max1(float v, float* red) {
+  v = warp_max(v);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float s = red[0];
+#pragma unroll
+  for (int w = 1; w < NW; ++w) s = fmaxf(s, red[w]);
+  __syncthreads();
+  return s;
+}
+// thread holds 4 channels (4q..4q+3, q = tid & 3) of a 16-vector partial sum -> out16[16]
+__device__ __forceinline__ void block_sum_q4(float4 v, float* red, float* out16) {
+#pragma unroll
+  for (int o = 4; o < 32; o <<= 1) {
+    v.x += __shfl_xor_sync(0xffffffffu, v.x, o);
+    v.y += __shfl_xor_sync(0xffffffffu, v.y, o);
+    v.z += __shfl_xor_sync(0xffffffffu, v.z, o);
+    v.w += __shfl_xor_sync(0xffffffffu, v.w, o);
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane < 4) st4(red + warp * 16 + lane * 4, v);
+  __syncthreads();
+  if (threadIdx.x < 16) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) s += red[w * 16 + threadIdx.x];
+    out16[threadIdx.x] = s;
+  }
+  __syncthreads();
+}
+
+// y[row] = act(b[row] + W[row][:] . x) for row < rows; 8 lanes per row; rows must be a multiple of 4.
+// W, b in global memory (read through L1/L2), x and y in shared memory.  No barrier inside.
+template <bool TANH>
+__device__ __forceinline__ void matvec8(const float* __restrict__ W, const float* __restrict__ b, int rows, int cols,
+                                        const float* x, float* y) {
+  const int p = threadIdx.x & 7;
+  for (int row = threadIdx.x >> 3; row < rows; row += NT / 8) {
+    const float* w = W + (size_t)row * cols;
+    float acc = 0.f;
+    for (int k = p; k < cols; k += 8) acc = fmaf(__ldg(w + k), x[k], acc);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+    if (p == 0) {
+      acc += __ldg(b + row);
+      y[row] = TANH ? tanhf(acc) : acc;
+    }
+  }
+}
+
+// ---- once per launch: parameters -> shared memory (with the composed attention projections) --------------
+__device__ __forceinline__ void load_weights(const float* __restrict__ P, float* sW) {
+  const int t = threadIdx.x;
+  for (int i = t; i < 384; i += NT) {
+    const int f = i >> 4, c = i & 15;
+    sW[S_WET + i] = f < F ? P[P_ENC_W + c * F + f] : 0.f;
+  }
+  if (t < 16) sW[S_BE + t] = P[P_ENC_B + t];
+  for (int i = t; i < 512; i += NT) {
+    const int o = i >> 4, c = i & 15;
+    const int src = o < 16 ? o * 32 + c : (o - 16) * 32 + 16 + c;
+    sW[S_WPQ0 + i] = P[P_GCN0_W + src];
+    sW[S_WPQ1 + i] = P[P_GCN1_W + src];
+  }
+  if (t < 16) {
+    sW[S_B0 + t] = P[P_GCN0_B + t];
+    sW[S_B1 + t] = P[P_GCN1_B + t];
+    sW[S_BO + t] = P[P_MHA_OUT_B + t];
+  }
+  for (int i = t; i < 256; i += NT) {
+    const int r = i >> 4, c = i & 15;
+    float q = 0.f, k = 0.f, v = 0.f;
+#pragma unroll 4
+    for (int m = 0; m < 16; ++m) {
+      q = fmaf(P[P_MHA_IN_W + r * 16 + m], P[P_ATT_Q_W + m * 16 + c], q);
+      k = fmaf(P[P_MHA_IN_W + (16 + r) * 16 + m], P[P_ATT_K_W + m * 16 + c], k);
+      v = fmaf(P[P_MHA_IN_W + (32 + r) * 16 + m], P[P_ATT_V_W + m * 16 + c], v);
+    }
+    sW[S_QC + i] = q;
+    sW[S_KC + i] = k;
+    sW[S_VC + i] = v;
+    sW[S_WO + i] = P[P_MHA_OUT_W + i];
+  }
+  if (t < 16) {
+    float q = P[P_MHA_IN_B + t], v = P[P_MHA_IN_B + 32 + t];
+    for (int m = 0; m < 16; ++m) {
+      q = fmaf(P[P_MHA_IN_W + t * 16 + m], P[P_ATT_Q_B + m], q);
+      v = fmaf(P[P_MHA_IN_W + (32 + t) * 16 + m], P[P_ATT_V_B + m], v);
+    }
+    sW[S_QBC + t] = q;
+    sW[S_VBC + t] = v;
+  }
+  for (int i = t; i < 2048; i += NT) sW[S_LUW0 + i] = P[P_LU_W0 + i];
+  for (int i = t; i < 512; i += NT) {
+    const float w = P[P_RD_W0 + i];
+    sW[S_RDW0 + i] = w;
+    sW[S_RDW0T + (i & 15) * 32 + (i >> 4)] = w;
+  }
+  if (t < 32) {
+    sW[S_LUB0 + t] = P[P_LU_B0 + t];
+    sW[S_LUW1 + t] = P[P_LU_W1 + t];
+    sW[S_RDB0 + t] = P[P_RD_B0 + t];
+    sW[S_RDW1 + t] = P[P_RD_W1 + t];
+  }
+}
+
+// ---- per-graph view ---------------------------------------------------------------------------------------
+struct GraphView {
+  int n, e, k, stage, gid;
+  const float* x;          // [n][24] global
+  float* H0g;              // [n][16] global scratch: h^0
+  float* H1g;              // [n][16] global scratch: h^1
+  float* EPQ;              // [n][32]
+  float* GPQ;              // [n][32]
+  float* H;                // [n][16]
+  float* inv;              // [n]
+  float* alpha;            // [n]
+  float* z;                // [k]
+  float* gz;               // [k]
+  float* ghead;            // [k][16]
+  const uint16_t* rp;      // [n+1]
+  const uint32_t* adj;     // [2e]
+  const uint32_t* cuv;     // [k]
+  const int* cidx;         // [k]
+};
+
+// exp-transformed edge-MLP pre-activations of one layer: EPQ[i][o] = exp(2 (Wpq[o] . h_i + b[o]))  (b only for o<16)
+__device__ __forceinline__ void epq_phase(const GraphView& g, const float* hsrc, const float* Wpq, const float* b) {
+  for (int task = threadIdx.x; task < g.n * 8; task += NT) {
+    const int i = task >> 3, og = task & 7;
+    const float4 h0 = ld4(hsrc + i * 16), h1 = ld4(hsrc + i * 16 + 4), h2 = ld4(hsrc + i * 16 + 8),
+                 h3 = ld4(hsrc + i * 16 + 12);
+    float out[4];
+#pragma unroll
+    for (int oo = 0; oo < 4; ++oo) {
+      const int o = og * 4 + oo;
+      const float* w = Wpq + o * 16;
+      float s = o < 16 ? b[o] : 0.f;
+      s += dot4(ld4(w), h0);
+      s += dot4(ld4(w + 4), h1);
+      s += dot4(ld4(w + 8), h2);
+      s += dot4(ld4(w + 12), h3);
+      out[oo] = exp2a(s);
+    }
+    st4(g.EPQ + i * 32 + og * 4, make_float4(out[0], out[1], out[2], out[3]));
+  }
+}
+
+// hidden activations of the policy head for one candidate (warp-wide; lane = hidden unit).
+// Returns t (this lane's tanh unit) and xin (the candidate's input channel `lane & 15`).
+__device__ __forceinline__ void head_unit(const GraphView& g, int j, const float (&wrow)[16], float cb, float& t,
+                                          float& xin) {
+  const int c16 = threadIdx.x & 15;
+  const uint32_t uv = g.cuv[j];
+  if (g.stage == 0) {
+    const int u = uv & 0xffffu, v = uv >> 16;
+    const float epu = g.EPQ[u * 32 + c16], equ = g.EPQ[u * 32 + 16 + c16];
+    const float epv = g.EPQ[v * 32 + c16], eqv = g.EPQ[v * 32 + 16 + c16];
+    const float r1 = rcp_approx(fmaf(epu, eqv, 1.f)), r2 = rcp_approx(fmaf(epv, equ, 1.f));
+    xin = (1.f - r1) - r2;
+  } else {
+    xin = g.H[(int)uv * 16 + c16];
+  }
+  float pre = cb;
+#pragma unroll
+  for (int c = 0; c < 16; ++c) pre = fmaf(wrow[c], __shfl_sync(0xffffffffu, xin, c), pre);
+  t = tanhf(pre);
+}
+
+// own-thread read-modify-write on this CTA's private gradient row (same thread always owns the same element)
+__device__ __forceinline__ void gacc(float* gp, int idx, float v) { gp[idx] += v; }
+
+template <bool TRAIN, bool BIG>
+__device__ void graph_body(const StepArgs& a, const BlobHeader& hd, const GraphDesc& d, int gid, float* smem,
+                           float* gp, float* scr) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int q = tid & 3;
+  float* sW = smem;
+  float* sV = smem + S_VEC;
+  float* sRed = smem + S_RED;
+  float* sc = sV + V_SC;
+  const float* P = a.params;
+
+  GraphView g;
+  g.n = d.n; g.e = d.e; g.k = d.k; g.stage = d.stage; g.gid = gid;
+  g.x = reinterpret_cast<const float*>(a.blob + hd.off_x) + (size_t)d.x_row * FS;
+  const float* gnum = reinterpret_cast<const float*>(a.blob + hd.off_num) + (size_t)gid * NUMD;
+  const float* gcur = reinterpret_cast<const float*>(a.blob + hd.off_cur) + (size_t)gid * FS;
+  const uint16_t* rp_g = reinterpret_cast<const uint16_t*>(a.blob + hd.off_rowptr) + d.rp_off;
+  const uint32_t* adj_g = reinterpret_cast<const uint32_t*>(a.blob + hd.off_adj) + d.adj_off;
+  const uint32_t* cuv_g = reinterpret_cast<const uint32_t*>(a.blob + hd.off_cand_uv) + d.cand_off;
+  const int* cidx_g = reinterpret_cast<const int*>(a.blob + hd.off_cand_idx) + d.cand_off;
+  const int n = g.n, e = g.e, k = g.k;
+  g.H0g = scr;
+  g.H1g = scr + (size_t)a.n_cap * 16;
+  if constexpr (BIG) {
+    float* b = scr + (size_t)a.n_cap * 32;
+    g.EPQ = b;  b += (size_t)a.n_cap * 32;
+    g.GPQ = b;  b += (size_t)a.n_cap * 32;
+    g.H = b;    b += (size_t)a.n_cap * 16;
+    g.inv = b;  b += a.n_cap;
+    g.alpha = b; b += a.n_cap;
+    const size_t kcap = (size_t)(a.e_cap > a.n_cap ? a.e_cap : a.n_cap);
+    g.z = b;    b += kcap;
+    g.gz = b;   b += kcap;
+    g.ghead = b;
+    g.rp = rp_g; g.adj = adj_g; g.cuv = cuv_g; g.cidx = cidx_g;
+  } else {
+    g.EPQ = smem + S_EPQ; g.GPQ = smem + S_GPQ; g.H = smem + S_H; g.inv = smem + S_INV;
+    g.alpha = smem + S_ALPHA; g.z = smem + S_Z; g.gz = smem + S_GZ; g.ghead = smem + S_GHEAD;
+    uint16_t* rp_s = reinterpret_cast<uint16_t*>(smem + S_RP);
+    uint32_t* adj_s = reinterpret_cast<uint32_t*>(smem + S_ADJ);
+    uint32_t* cuv_s = reinterpret_cast<uint32_t*>(smem + S_CUV);
+    int* cidx_s = reinterpret_cast<int*>(smem + S_CIDX);
+    // stage the graph's neighbourhood lists in shared memory (16-byte vectors; blob sections are padded)
+    {
+      const uint4* s0 = reinterpret_cast<const uint4*>(rp_g);
+      uint4* d0 = reinterpret_cast<uint4*>(rp_s);
+      for (int i = tid; i < (n + 1 + 7) / 8; i += NT) d0[i] = s0[i];
+      const uint4* s1 = reinterpret_cast<const uint4*>(adj_g);
+      uint4* d1 = reinterpret_cast<uint4*>(adj_s);
+      for (int i = tid; i < (2 * e + 3) / 4; i += NT) d1[i] = s1[i];
+      const uint4* s2 = reinterpret_cast<const uint4*>(cuv_g);
+      const uint4* s3 = reinterpret_cast<const uint4*>(cidx_g);
+      uint4* d2 = reinterpret_cast<uint4*>(cuv_s);
+      uint4* d3 = reinterpret_cast<uint4*>(cidx_s);
+      for (int i = tid; i < (k + 3) / 4; i += NT) { d2[i] = s2[i]; d3[i] = s3[i]; }
+    }
+    g.rp = rp_s; g.adj = adj_s; g.cuv = cuv_s; g.cidx = cidx_s;
+  }
+  if (tid < NUMD) sV[V_X52 + tid] = gnum[tid];
+  if (tid >= 64 && tid < 64 + FS) sV[V_XCUR + tid - 64] = gcur[tid - 64];
+  if (tid < 24) sc[tid] = 0.f;
+  __syncthreads();
+
+  // ================================================================================ forward
+  for (int i = tid; i < n; i += NT) g.inv[i] = 1.0f / ((float)(g.rp[i + 1] - g.rp[i]) + EPS_DEG);
+  // h^0 = X We^T + be (state_encoder.py:189); 4 lanes per node, 4 channels per lane
+  for (int task = tid; task < n * 4; task += NT) {
+    const int i = task >> 2;
+    const float* xr = g.x + (size_t)i * FS;
+    float4 acc = ld4(sW + S_BE + q * 4);
+#pragma unroll
+    for (int f4i = 0; f4i < 6; ++f4i) {
+      const float4 xv = __ldg(reinterpret_cast<const float4*>(xr) + f4i);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float xs = comp(xv, j);
+        const float4 w = ld4(sW + S_WET + (f4i * 4 + j) * 16 + q * 4);
+        acc.x = fmaf(w.x, xs, acc.x); acc.y = fmaf(w.y, xs, acc.y);
+        acc.z = fmaf(w.z, xs, acc.z); acc.w = fmaf(w.w, xs, acc.w);
+      }
+    }
+    st4(g.H + i * 16 + q * 4, acc);
+    if (TRAIN) st4(g.H0g + i * 16 + q * 4, acc);
+  }
+  if (tid < 16) {   // current node through the same encoder (state_encoder.py:190-191)
+    float s = sW[S_BE + tid];
+    for (int f = 0; f < F; ++f) s = fmaf(sW[S_WET + f * 16 + tid], sV[V_XCUR + f], s);
+    sV[V_HC + tid] = s;
+  }
+  // numeric feature encoder, first layer (state_encoder.py:35-57,187)
+  matvec8<true>(P + P_NUM_W0, P + P_NUM_B0, NH0, NUMD, sV + V_X52, sV + V_A0);
+  __syncthreads();
+  matvec8<true>(P + P_NUM_W1, P + P_NUM_B1, 16, NH0, sV + V_A0, sV + V_SV);
+
+  // GCN layers (state_encoder.py:194-197): h <- h + (sum_{nbr} he) / (deg + eps), pull over the CSR
+  for (int l = 0; l < 2; ++l) {
+    epq_phase(g, g.H, sW + (l == 0 ? S_WPQ0 : S_WPQ1), sW + (l == 0 ? S_B0 : S_B1));
+    __syncthreads();
+    float4 msum = f4(0.f), hsum = f4(0.f);
+    for (int task = tid; task < n * 4; task += NT) {
+      const int i = task >> 2;
+      const float4 epi = ld4(g.EPQ + i * 32 + q * 4), eqi = ld4(g.EPQ + i * 32 + 16 + q * 4);
+      const int beg = g.rp[i], end = g.rp[i + 1];
+      float4 acc = f4(0.f);
+      for (int t = beg; t < end; ++t) {
+        const int kk = g.adj[t] & 0xffffu;
+        const float4 epk = ld4(g.EPQ + kk * 32 + q * 4), eqk = ld4(g.EPQ + kk * 32 + 16 + q * 4);
+        acc.x += (1.f - rcp_approx(fmaf(epi.x, eqk.x, 1.f))) - rcp_approx(fmaf(epk.x, eqi.x, 1.f));
+        acc.y += (1.f - rcp_approx(fmaf(epi.y, eqk.y, 1.f))) - rcp_approx(fmaf(epk.y, eqi.y, 1.f));
+        acc.z += (1.f - rcp_approx(fmaf(epi.z, eqk.z, 1.f))) - rcp_approx(fmaf(epk.z, eqi.z, 1.f));
+        acc.w += (1.f - rcp_approx(fmaf(epi.w, eqk.w, 1.f))) - rcp_approx(fmaf(epk.w, eqi.w, 1.f));
+      }
+      const float iv = g.inv[i];
+      float4 h = ld4(g.H + i * 16 + q * 4);
+      h.x = fmaf(acc.x, iv, h.x); h.y = fmaf(acc.y, iv, h.y); h.z = fmaf(acc.z, iv, h.z); h.w = fmaf(acc.w, iv, h.w);
+      st4(g.H + i * 16 + q * 4, h);
+      if (l == 0) {
+        if (TRAIN) st4(g.H1g + i * 16 + q * 4, h);
+      } else {
+        msum = msum + acc;
+        hsum = hsum + h;
+      }
+    }
+    if (l == 1) {   // masked means (state_encoder.py:179-182,199-200); sum_j he_j = 1/2 sum_i acc_i
+      block_sum_q4(msum, sRed, sV + V_TMP16);
+      block_sum_q4(hsum, sRed, sV + V_TMP16B);
+      if (tid < 16) {
+        sV[V_SV + 16 + tid] = sV[V_TMP16B + tid] / (float)n;
+        sV[V_SV + 32 + tid] = (0.5f * sV[V_TMP16 + tid]) / (float)e;
+      }
+    }
+    __syncthreads();
+  }
+
+  // attention of the current node over all nodes (state_encoder.py:150-161)
+  if (tid < 16) {
+    float s = sW[S_QBC + tid];
+    for (int c = 0; c < 16; ++c) s = fmaf(sW[S_QC + tid * 16 + c], sV[V_HC + c], s);
+    sV[V_QP + tid] = s;
+  }
+  __syncthreads();
+  if (tid < 16) {
+    float s = 0.f;
+    for (int r = 0; r < 16; ++r) s = fmaf(sW[S_KC + r * 16 + tid], sV[V_QP + r], s);
+    sV[V_QK + tid] = 0.25f * s;     // 1/sqrt(head_dim)
+  }
+  __syncthreads();
+  {
+    const float4 qk4 = ld4(sV + V_QK + q * 4);
+    float lmax = -CUDART_INF_F;
+    for (int task = tid; task < ((n * 4 + 31) & ~31); task += NT) {
+      const int i = task >> 2;
+      float s = i < n ? dot4(qk4, ld4(g.H + i * 16 + q * 4)) : 0.f;
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      if (i < n) {
+        if (q == 0) g.alpha[i] = s;
+        lmax = fmaxf(lmax, s);
+      }
+    }
+    const float smax = block_max1(lmax, sRed);   // barrier inside also publishes alpha
+    float4 hb = f4(0.f);
+    float asum = 0.f;
+    for (int task = tid; task < n * 4; task += NT) {
+      const int i = task >> 2;
+      const float ai = expf(g.alpha[i] - smax);
+      hb = hb + ld4(g.H + i * 16 + q * 4) * ai;
+      if (q == 0) asum += ai;
+    }
+    __syncthreads();                              // everyone has read alpha (scores) before it becomes weights
+    for (int i = tid; i < n; i += NT) g.alpha[i] = expf(g.alpha[i] - smax);
+    const float Z = block_sum1(asum, sRed);
+    block_sum_q4(hb, sRed, sV + V_TMP16);
+    if (tid < 16) sV[V_HBAR + tid] = sV[V_TMP16 + tid] / Z;
+    if (tid == 0) sc[SC_Z] = Z;
+    __syncthreads();
+  }
+  if (tid < 16) {
+    float s = sW[S_VBC + tid];
+    for (int c = 0; c < 16; ++c) s = fmaf(sW[S_VC + tid * 16 + c], sV[V_HBAR + c], s);
+    sV[V_VP + tid] = s;
+  }
+  __syncthreads();
+  if (tid < 16) {
+    float s = sW[S_BO + tid];
+    for (int c = 0; c < 16; ++c) s = fmaf(sW[S_WO + tid * 16 + c], sV[V_VP + c], s);
+    sV[V_SV + 48 + tid] = s;
+  }
+  if (tid < 3) sV[V_SV + 64 + tid] = (tid == g.stage) ? 1.f : 0.f;
+  __syncthreads();
+
+  // value head (value.py:15-39)
+  matvec8<true>(P + P_VAL_W0, P + P_VAL_B0, HID, SVD, sV + V_SV, sV + V_Y0);
+  __syncthreads();
+  matvec8<true>(P + P_VAL_W1, P + P_VAL_B1, HID, HID, sV + V_Y0, sV + V_Y1);
+  __syncthreads();
+  if (warp == 0) {
+    const float v = warp_sum(__ldg(P + P_VAL_W2 + lane) * sV[V_Y1 + lane]) + __ldg(P + P_VAL_B2);
+    if (lane == 0) sc[SC_VALUE] = v;
+  }
+
+  // policy head on the mask-true candidates of the active stage (policy.py:45-65)
+  float wrow[16];
+  float cb, w2;
+  if (g.stage == 0) {
+    {   // Weff = Wa + Wd + Wc diag(hc), ceff = b + (Wb - Wd) hc   (state_encoder.py:207-210 folded into the head)
+      const int r = tid >> 4, c = tid & 15;
+      const float* w = sW + S_LUW0 + r * 64;
+      sV[V_WEFFT + c * 32 + r] = w[c] + w[48 + c] + w[32 + c] * sV[V_HC + c];
+      if (tid < 32) {
+        const float* wr = sW + S_LUW0 + tid * 64;
+        float s = sW[S_LUB0 + tid];
+        for (int cc = 0; cc < 16; ++cc) s = fmaf(wr[16 + cc] - wr[48 + cc], sV[V_HC + cc], s);
+        sV[V_CEFF + tid] = s;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < 16; ++c) wrow[c] = sV[V_WEFFT + c * 32 + lane];
+    cb = sV[V_CEFF + lane];
+    w2 = sW[S_LUW1 + lane];
+  } else {
+#pragma unroll
+    for (int c = 0; c < 16; ++c) wrow[c] = sW[S_RDW0T + c * 32 + lane];
+    cb = sW[S_RDB0 + lane];
+    w2 = sW[S_RDW1 + lane];
+  }
+  for (int j = warp; j < k; j += NW) {
+    float t, xin;
+    head_unit(g, j, wrow, cb, t, xin);
+    const float zj = warp_sum(w2 * t);
+    if (lane == 0) g.z[j] = zj;
+  }
+  __syncthreads();
+  {   // masked softmax statistics: log-softmax over the candidates equals log-softmax over all padded logits
+    float lmax = -CUDART_INF_F;
+    int lbest = 0x7fffffff;
+    for (int j = tid; j < k; j += NT) {
+      const float zj = g.z[j];
+      if (zj > lmax) { lmax = zj; lbest = j; }
+    }
+    // block arg-max with first-index tie break (policy.py:72 `probs.argmax`)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float om = __shfl_xor_sync(0xffffffffu, lmax, o);
+      const int ob = __shfl_xor_sync(0xffffffffu, lbest, o);
+      if (om > lmax || (om == lmax && ob < lbest)) { lmax = om; lbest = ob; }
+    }
+    if (lane == 0) { sRed[warp] = lmax; sRed[NW + warp] = __int_as_float(lbest); }
+    __syncthreads();
+    float zmax = sRed[0];
+    int best = __float_as_int(sRed[NW]);
+    for (int w = 1; w < NW; ++w) {
+      const float om = sRed[w];
+      const int ob = __float_as_int(sRed[NW + w]);
+      if (om > zmax || (om == zmax && ob < best)) { zmax = om; best = ob; }
+    }
+    __syncthreads();
+    float lsum = 0.f;
+    for (int j = tid; j < k; j += NT) lsum += expf(g.z[j] - zmax);
+    const float ssum = block_sum1(lsum, sRed);
+    const float lse = zmax + logf(ssum);
+    float lent = 0.f;
+    int aidx = -1;
+    if (a.actions) aidx = (int)a.actions[(size_t)gid * 2 + g.stage];
+    for (int j = tid; j < k; j += NT) {
+      const float lp = g.z[j] - lse;
+      lent -= expf(lp) * lp;
+      if (g.cidx[j] == aidx) sc[SC_SLOT] = (float)(j + 1);
+    }
+    const float ent = block_sum1(lent, sRed);    // barriers inside publish SC_SLOT
+    if (tid == 0) {
+      float logp = 0.f, H = ent;
+      int greedy = 0;
+      const int slot = (int)sc[SC_SLOT] - 1;
+      if (k > 0) {
+        greedy = g.cidx[best];
+        if (a.actions) logp = slot >= 0 ? g.z[slot] - lse : MASK_FILL - lse;
+      } else {      // every logit equals the fill value: uniform over the padded width
+        const float cap = (float)(g.stage == 0 ? hd.e_cap : hd.n_cap);
+        H = logf(cap);
+        if (a.actions) logp = -logf(cap);
+      }
+      sc[SC_LSE] = lse; sc[SC_ENT] = H; sc[SC_LOGP] = logp;
+      if (a.out_value) a.out_value[gid] = sc[SC_VALUE];
+      if (a.out_logp) a.out_logp[gid] = logp;
+      if (a.out_entropy) a.out_entropy[gid] = H;
+      if (a.out_greedy) a.out_greedy[gid] = greedy;
+    }
+    __syncthreads();
+  }
+  if constexpr (!TRAIN) return;
+
+  // ================================================================================ backward
+  if (tid == 0) {
+    const float V = sc[SC_VALUE], R = a.ret[gid], logp = sc[SC_LOGP], H = sc[SC_ENT];
+    const float dv = V - R;
+    float glp = 0.f, gH = 0.f, surr = 0.f, negent = 0.f, in_ind = 0.f;
+    if (a.exps[gid] != 0.f) {
+      in_ind = 1.f;
+      const float r = expf(logp - a.fixed_lp[gid]), A = a.adv[gid];
+      const float lo = 1.f - a.clip_eps, hi = 1.f + a.clip_eps;
+      const float s1 = r * A, s2 = fminf(fmaxf(r, lo), hi) * A;
+      surr = -fminf(s1, s2);
+      if ((r >= lo && r <= hi) || s1 < s2) glp = -A * r * a.inv_ind;
+      gH = -a.c_entropy * a.inv_ind;
+      negent = -H;
+    }
+    sc[SC_GV] = 2.f * a.c_value * dv * a.inv_batch;
+    sc[SC_GLP] = glp;
+    sc[SC_GH] = gH;
+    float* st = gp + G_STATS;
+    st[0] += dv * dv; st[1] += surr; st[2] += negent; st[3] += 1.f; st[4] += in_ind;
+    st[5] += g.stage == 0 ? 1.f : 0.f; st[6] += g.stage == 1 ? 1.f : 0.f;
+    st[7] += (isfinite(V) && isfinite(logp) && isfinite(H)) ? 0.f : 1.f;
+  }
+  __syncthreads();
+  {   // logits gradient: g_z = g_lp (delta_a - p) - g_H p (logp + H)
+    const float glp = sc[SC_GLP], gH = sc[SC_GH], lse = sc[SC_LSE], H = sc[SC_ENT];
+    const int slot = (int)sc[SC_SLOT] - 1;
+    for (int j = tid; j < k; j += NT) {
+      const float lp = g.z[j] - lse, p = expf(lp);
+      g.gz[j] = glp * ((j == slot ? 1.f : 0.f) - p) - gH * p * (lp + H);
+    }
+  }
+  if (tid < 16) sV[V_GHC + tid] = 0.f;
+  __syncthreads();
+
+  // ---- policy head backward, CH candidates at a time (chunk buffers alias the GPQ region / shared scratch)
+  {
+    float* cGU = smem + S_GPQ;              // [CH][32] g_u
+    float* cGT = cGU + CH * 32;             // [CH][32] g_z * t
+    float* cX = cGT + CH * 32;              // [CH][16] head input
+    float G = 0.f, gcr = 0.f, gw2r = 0.f;   // thread (r = tid>>4, c = tid&15)
+    const int r_ = tid >> 4, c_ = tid & 15;
+    const float* WT = g.stage == 0 ? sV + V_WEFFT : sW + S_RDW0T;   // [16][32]
+    for (int base = 0; base < k; base += CH) {
+      const int cn = min(CH, k - base);
+      for (int jj = warp; jj < cn; jj += NW) {
+        float t, xin;
+        head_unit(g, base + jj, wrow, cb, t, xin);
+        const float gzj = g.gz[base + jj];
+        cGU[jj * 32 + lane] = gzj * w2 * (1.f - t * t);
+        cGT[jj * 32 + lane] = gzj * t;
+        if (lane < 16) cX[jj * 16 + lane] = xin;
+      }
+      __syncthreads();
+      for (int jj = 0; jj < cn; ++jj) {
+        const float gu = cGU[jj * 32 + r_];
+        G = fmaf(gu, cX[jj * 16 + c_], G);
+        if (c_ == 0) { gcr += gu; gw2r += cGT[jj * 32 + r_]; }
+      }
+      for (int task = tid; task < cn * 16; task += NT) {   // g_x = W^T g_u
+        const int jj = task >> 4, c = task & 15;
+        float s = 0.f;
+#pragma unroll 8
+        for (int r = 0; r < 32; ++r) s = fmaf(WT[c * 32 + r], cGU[jj * 32 + r], s);
+        g.ghead[(size_t)(base + jj) * 16 + c] = s;
+      }
+      __syncthreads();
+    }
+    sV[V_GWEFF + tid] = G;
+    if (c_ == 0) { sV[V_GC + r_] = gcr; sV[V_GW2 + r_] = gw2r; }
+    __syncthreads();
+    if (g.stage == 0) {
+      const float hc = sV[V_HC + c_], gc = sV[V_GC + r_];
+      const int o = P_LU_W0 + r_ * 64 + c_;
+      gacc(gp, o, G);
+      gacc(gp, o + 16, gc * hc);
+      gacc(gp, o + 32, G * hc);
+      gacc(gp, o + 48, G - gc * hc);
+      if (tid < 32) { gacc(gp, P_LU_B0 + tid, sV[V_GC + tid]); gacc(gp, P_LU_W1 + tid, sV[V_GW2 + tid]); }
+      if (tid < 16) {   // d/d hc through ceff and through Wc diag(hc)
+        float s = 0.f;
+        for (int r = 0; r < 32; ++r) {
+          const float* w = sW + S_LUW0 + r * 64;
+          s = fmaf(w[16 + tid] - w[48 + tid], sV[V_GC + r], s);
+          s = fmaf(w[32 + tid], sV[V_GWEFF + r * 16 + tid], s);
+        }
+        sV[V_GHC + tid] = s;
+      }
+    } else {
+      gacc(gp, P_RD_W0 + tid, G);
+      if (tid < 32) { gacc(gp, P_RD_B0 + tid, sV[V_GC + tid]); gacc(gp, P_RD_W1 + tid, sV[V_GW2 + tid]); }
+    }
+  }
+
+  // ---- value head backward (value.py:36-39)
+  if (tid < 32) sV[V_D1 + tid] = sc[SC_GV] * __ldg(P + P_VAL_W2 + tid) * (1.f - sV[V_Y1 + tid] * sV[V_Y1 + tid]);
+  __syncthreads();
+  if (tid < 32) {
+    float s = 0.f;
+    for (int r = 0; r < 32; ++r) s = fmaf(__ldg(P + P_VAL_W1 + r * 32 + tid), sV[V_D1 + r], s);
+    sV[V_D0 + tid] = s * (1.f - sV[V_Y0 + tid] * sV[V_Y0 + tid]);
+  }
+  __syncthreads();
+  if (tid < SVD) {
+    float s = 0.f;
+    for (int r = 0; r < 32; ++r) s = fmaf(__ldg(P + P_VAL_W0 + r * SVD + tid), sV[V_D0 + r], s);
+    sV[V_GSV + tid] = s;
+  }
+  for (int idx = tid; idx < HID * SVD; idx += NT) gacc(gp, P_VAL_W0 + idx, sV[V_D0 + idx / SVD] * sV[V_SV + idx % SVD]);
+  for (int idx = tid; idx < HID * HID; idx += NT) gacc(gp, P_VAL_W1 + idx, sV[V_D1 + (idx >> 5)] * sV[V_Y0 + (idx & 31)]);
+  if (tid < 32) {
+    gacc(gp, P_VAL_B0 + tid, sV[V_D0 + tid]);
+    gacc(gp, P_VAL_B1 + tid, sV[V_D1 + tid]);
+    gacc(gp, P_VAL_W2 + tid, sc[SC_GV] * sV[V_Y1 + tid]);
+  }
+  if (tid == 32) gacc(gp, P_VAL_B2, sc[SC_GV]);
+  __syncthreads();
+  // ---- numeric encoder backward
+  if (tid < 16) sV[V_DN1 + tid] = sV[V_GSV + tid] * (1.f - sV[V_SV + tid] * sV[V_SV + tid]);
+  __syncthreads();
+  if (tid < NH0) {
+    float s = 0.f;
+    for (int r = 0; r < 16; ++r) s = fmaf(__ldg(P + P_NUM_W1 + r * NH0 + tid), sV[V_DN1 + r], s);
+    sV[V_DN0 + tid] = s * (1.f - sV[V_A0 + tid] * sV[V_A0 + tid]);
+  }
+  __syncthreads();
+  for (int idx = tid; idx < 16 * NH0; idx += NT) gacc(gp, P_NUM_W1 + idx, sV[V_DN1 + (idx >> 6)] * sV[V_A0 + (idx & 63)]);
+  for (int idx = tid; idx < NH0 * NUMD; idx += NT) gacc(gp, P_NUM_W0 + idx, sV[V_DN0 + idx / NUMD] * sV[V_X52 + idx % NUMD]);
+  if (tid < 16) gacc(gp, P_NUM_B1 + tid, sV[V_DN1 + tid]);
+  if (tid < NH0) gacc(gp, P_NUM_B0 + tid, sV[V_DN0 + tid]);
+
+  // ---- attention backward
+  if (tid < 16) {   // g_v' = Wo^T g_att
+    float s = 0.f;
+    for (int r = 0; r < 16; ++r) s = fmaf(sW[S_WO + r * 16 + tid], sV[V_GSV + 48 + r], s);
+    sV[V_GVP + tid] = s;
+    sV[V_GMN + tid] = sV[V_GSV + 16 + tid] / (float)n;
+    sV[V_CE + tid] = e > 0 ? sV[V_GSV + 32 + tid] / (float)e : 0.f;
+  }
+  __syncthreads();
+  if (tid < 16) {   // g_hbar = Vc^T g_v'
+    float s = 0.f;
+    for (int r = 0; r < 16; ++r) s = fmaf(sW[S_VC + r * 16 + tid], sV[V_GVP + r], s);
+    sV[V_GHBAR + tid] = s;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    float s = 0.f;
+    for (int c = 0; c < 16; ++c) s = fmaf(sV[V_GHBAR + c], sV[V_HBAR + c], s);
+    sc[SC_GDOT] = s;
+  }
+  __syncthreads();
+  {
+    const float4 gh4 = ld4(sV + V_GHBAR + q * 4), qk4 = ld4(sV + V_QK + q * 4), gmn4 = ld4(sV + V_GMN + q * 4);
+    const float invZ = 1.f / sc[SC_Z], gdot = sc[SC_GDOT];
+    float4 gsh = f4(0.f);
+    for (int task = tid; task < ((n * 4 + 31) & ~31); task += NT) {
+      const int i = task >> 2;
+      const float4 h = i < n ? ld4(g.H + i * 16 + q * 4) : f4(0.f);
+      float dp = dot4(gh4, h);
+      dp += __shfl_xor_sync(0xffffffffu, dp, 1);
+      dp += __shfl_xor_sync(0xffffffffu, dp, 2);
+      if (i < n) {
+        const float ai = g.alpha[i] * invZ;
+        const float gs = ai * (dp - gdot);
+        gsh = gsh + h * gs;
+        // g_h^L = g_mean/n + a_i g_hbar (value path) + g_s qk (key path); in place over h^L
+        st4(g.H + i * 16 + q * 4, gmn4 + gh4 * ai + qk4 * gs);
+      }
+    }
+    block_sum_q4(gsh, sRed, sV + V_GSH);
+  }
+  if (tid < 16) {   // g_q' = Kc gsh / 4
+    float s = 0.f;
+    for (int c = 0; c < 16; ++c) s = fmaf(sW[S_KC + tid * 16 + c], sV[V_GSH + c], s);
+    sV[V_GQP + tid] = 0.25f * s;
+  }
+  __syncthreads();
+  if (tid < 16) {   // g_hc += Qc^T g_q'
+    float s = sV[V_GHC + tid];
+    for (int r = 0; r < 16; ++r) s = fmaf(sW[S_QC + r * 16 + tid], sV[V_GQP + r], s);
+    sV[V_GHC + tid] = s;
+  }
+  if (tid < 256) {
+    const int r = tid >> 4, c = tid & 15;
+    gacc(gp, G_QC + tid, sV[V_GQP + r] * sV[V_HC + c]);
+    gacc(gp, G_KC + tid, 0.25f * sV[V_QP + r] * sV[V_GSH + c]);
+    gacc(gp, G_VC + tid, sV[V_GVP + r] * sV[V_HBAR + c]);
+    gacc(gp, P_MHA_OUT_W + tid, sV[V_GSV + 48 + r] * sV[V_VP + c]);
+  }
+  if (tid < 16) {
+    gacc(gp, G_QBC + tid, sV[V_GQP + tid]);
+    gacc(gp, G_VBC + tid, sV[V_GVP + tid]);
+    gacc(gp, P_MHA_OUT_B + tid, sV[V_GSV + 48 + tid]);
+  }
+  if (g.stage == 1) {   // road head feeds h^L of its candidate nodes directly
+    for (int task = tid; task < k * 16; task += NT) {
+      const int j = task >> 4, c = task & 15;
+      g.H[(int)g.cuv[j] * 16 + c] += g.ghead[(size_t)j * 16 + c];
+    }
+  }
+  __syncthreads();
+
+  // ---- GCN layers, last to first
+  for (int l = 1; l >= 0; --l) {
+    const float* Wpq = sW + (l == 0 ? S_WPQ0 : S_WPQ1);
+    const float* hin = l == 0 ? g.H0g : g.H1g;     // layer input h^l (global scratch)
+    if (l == 0) {   // EPQ of layer 0 was overwritten by layer 1: recompute from h^0
+      epq_phase(g, hin, Wpq, sW + S_B0);
+      __syncthreads();
+    }
+    const bool last = (l == 1);
+    const float4 ce4 = last ? ld4(sV + V_CE + q * 4) : f4(0.f);
+    const bool use_head = last && g.stage == 0;
+    float4 bsum = f4(0.f);
+    for (int task = tid; task < n * 4; task += NT) {
+      const int i = task >> 2;
+      const float4 epi = ld4(g.EPQ + i * 32 + q * 4), eqi = ld4(g.EPQ + i * 32 + 16 + q * 4);
+      const float4 gsi = ld4(g.H + i * 16 + q * 4) * g.inv[i] + ce4;
+      const int beg = g.rp[i], end = g.rp[i + 1];
+      float4 aP = f4(0.f), aQ = f4(0.f);
+      for (int t = beg; t < end; ++t) {
+        const uint32_t ent = g.adj[t];
+        const int kk = ent & 0xffffu;
+        const float4 epk = ld4(g.EPQ + kk * 32 + q * 4), eqk = ld4(g.EPQ + kk * 32 + 16 + q * 4);
+        float4 ge = gsi + ld4(g.H + kk * 16 + q * 4) * g.inv[kk];
+        if (use_head && (ent >> 16)) ge = ge + ld4(g.ghead + (size_t)((ent >> 16) - 1) * 16 + q * 4);
+        float r;
+        // d tanh = 1 - t^2 = 4 r (1 - r);  g1 = ge/2 * (1 - t1^2) = 2 ge r1 (1 - r1)
+        r = rcp_approx(fmaf(epi.x, eqk.x, 1.f)); aP.x = fmaf(ge.x, 2.f * r * (1.f - r), aP.x);
+        r = rcp_approx(fmaf(epi.y, eqk.y, 1.f)); aP.y = fmaf(ge.y, 2.f * r * (1.f - r), aP.y);
+        r = rcp_approx(fmaf(epi.z, eqk.z, 1.f)); aP.z = fmaf(ge.z, 2.f * r * (1.f - r), aP.z);
+        r = rcp_approx(fmaf(epi.w, eqk.w, 1.f)); aP.w = fmaf(ge.w, 2.f * r * (1.f - r), aP.w);
+        r = rcp_approx(fmaf(epk.x, eqi.x, 1.f)); aQ.x = fmaf(ge.x, 2.f * r * (1.f - r), aQ.x);
+        r = rcp_approx(fmaf(epk.y, eqi.y, 1.f)); aQ.y = fmaf(ge.y, 2.f * r * (1.f - r), aQ.y);
+        r = rcp_approx(fmaf(epk.z, eqi.z, 1.f)); aQ.z = fmaf(ge.z, 2.f * r * (1.f - r), aQ.z);
+        r = rcp_approx(fmaf(epk.w, eqi.w, 1.f)); aQ.w = fmaf(ge.w, 2.f * r * (1.f - r), aQ.w);
+      }
+      st4(g.GPQ + i * 32 + q * 4, aP);
+      st4(g.GPQ + i * 32 + 16 + q * 4, aQ);
+      bsum = bsum + aP;
+    }
+    block_sum_q4(bsum, sRed, sV + V_TMP16);     // barriers inside: GPQ complete, EPQ dead
+    if (tid < 16) gacc(gp, (l == 0 ? P_GCN0_B : P_GCN1_B) + tid, sV[V_TMP16 + tid]);
+    {   // g_W[o][c] = sum_i GPQ[i][o] h^l[i][c]: 4x4 register tiles, K split over the 16 warps
+      float* redbuf = smem + S_EPQ;              // [NW][512]
+      const int to = lane >> 2, tc = lane & 3;
+      float acc[4][4];
+#pragma unroll
+      for (int x = 0; x < 4; ++x)
+#pragma unroll
+        for (int y = 0; y < 4; ++y) acc[x][y] = 0.f;
+      for (int i = warp; i < n; i += NW) {
+        const float4 gq = ld4(g.GPQ + i * 32 + to * 4);
+        const float4 hv = *reinterpret_cast<const float4*>(hin + (size_t)i * 16 + tc * 4);
+#pragma unroll
+        for (int x = 0; x < 4; ++x) {
+          const float gx = comp(gq, x);
+          acc[x][0] = fmaf(gx, hv.x, acc[x][0]); acc[x][1] = fmaf(gx, hv.y, acc[x][1]);
+          acc[x][2] = fmaf(gx, hv.z, acc[x][2]); acc[x][3] = fmaf(gx, hv.w, acc[x][3]);
+        }
+      }
+#pragma unroll
+      for (int x = 0; x < 4; ++x)
+        st4(redbuf + warp * 512 + (to * 4 + x) * 16 + tc * 4, make_float4(acc[x][0], acc[x][1], acc[x][2], acc[x][3]));
+    }
+    // g_h = g_h' + GPQ Wpq  (residual), in place
+    for (int task = tid; task < n * 4; task += NT) {
+      const int i = task >> 2;
+      float4 s = ld4(g.H + i * 16 + q * 4);
+#pragma unroll
+      for (int o4 = 0; o4 < 8; ++o4) {
+        const float4 gq = ld4(g.GPQ + i * 32 + o4 * 4);
+#pragma unroll
+        for (int x = 0; x < 4; ++x) {
+          const float gx = comp(gq, x);
+          const float4 w = ld4(Wpq + (o4 * 4 + x) * 16 + q * 4);
+          s.x = fmaf(gx, w.x, s.x); s.y = fmaf(gx, w.y, s.y); s.z = fmaf(gx, w.z, s.z); s.w = fmaf(gx, w.w, s.w);
+        }
+      }
+      st4(g.H + i * 16 + q * 4, s);
+    }
+    __syncthreads();
+    {
+      const float* redbuf = smem + S_EPQ;
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) s += redbuf[w * 512 + tid];
+      const int o = tid >> 4, c = tid & 15;
+      const int dst = o < 16 ? o * 32 + c : (o - 16) * 32 + 16 + c;
+      gacc(gp, (l == 0 ? P_GCN0_W : P_GCN1_W) + dst, s);
+    }
+    __syncthreads();
+  }
+
+  // ---- node encoder backward: g_We = g_h0^T X + g_hc x_cur^T, g_be = sum g_h0 + g_hc
+  {
+    float* redbuf = smem + S_EPQ;                // [NW][384]
+    const int tcc = lane / 6, tf = lane % 6;     // 4 channel tiles x 6 feature tiles (lanes 24..31 idle)
+    float acc[4][4];
+#pragma unroll
+    for (int x = 0; x < 4; ++x)
+#pragma unroll
+      for (int y = 0; y < 4; ++y) acc[x][y] = 0.f;
+    if (lane < 24) {
+      for (int i = warp; i < n; i += NW) {
+        const float4 gh = ld4(g.H + i * 16 + tcc * 4);
+        const float4 xv = __ldg(reinterpret_cast<const float4*>(g.x + (size_t)i * FS) + tf);
+#pragma unroll
+        for (int x = 0; x < 4; ++x) {
+          const float gx = comp(gh, x);
+          acc[x][0] = fmaf(gx, xv.x, acc[x][0]); acc[x][1] = fmaf(gx, xv.y, acc[x][1]);
+          acc[x][2] = fmaf(gx, xv.z, acc[x][2]); acc[x][3] = fmaf(gx, xv.w, acc[x][3]);
+        }
+      }
+#pragma unroll
+      for (int x = 0; x < 4; ++x)
+        st4(redbuf + warp * 384 + (tcc * 4 + x) * 24 + tf * 4, make_float4(acc[x][0], acc[x][1], acc[x][2], acc[x][3]));
+    }
+    float4 hs = f4(0.f);
+    for (int task = tid; task < n * 4; task += NT) hs = hs + ld4(g.H + (task >> 2) * 16 + q * 4);
+    block_sum_q4(hs, sRed, sV + V_TMP16);        // barriers inside publish redbuf
+    if (tid < 384) {
+      const int c = tid / 24, f = tid % 24;
+      if (f < F) {
+        float s = sV[V_GHC + c] * sV[V_XCUR + f];
+#pragma unroll
+        for (int w = 0; w < NW; ++w) s += redbuf[w * 384 + tid];
+        gacc(gp, P_ENC_W + c * F + f, s);
+      }
+    }
+    if (tid < 16) gacc(gp, P_ENC_B + tid, sV[V_TMP16 + tid] + sV[V_GHC + tid]);
+  }
+  __syncthreads();
+}
+
+template <bool TRAIN>
+__global__ void __launch_bounds__(NT, 1) k_sgnn(const __grid_constant__ StepArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  load_weights(a.params, smem);
+  float* gp = nullptr;
+  if constexpr (TRAIN) {
+    gp = a.gpart + (size_t)blockIdx.x * G_ROW;
+    for (int i = threadIdx.x; i < G_ROW; i += NT) gp[i] = 0.f;
+  }
+  __syncthreads();
+  const BlobHeader& hd = *reinterpret_cast<const BlobHeader*>(a.blob);
+  const GraphDesc* descs = reinterpret_cast<const GraphDesc*>(a.blob + hd.off_desc);
+  float* scr = a.scratch + (size_t)blockIdx.x * a.scratch_stride;
+  for (int item = blockIdx.x; item < a.count; item += gridDim.x) {
+    const int gid = a.ids ? a.ids[item] : item;
+    const GraphDesc d = descs[gid];
+    if (d.n > a.n_cap || d.e > a.e_cap || d.n < 1) {   // larger than the context was sized for: skip, flag
+      if (threadIdx.x == 0) {
+        if constexpr (TRAIN) gp[G_STATS + 7] += 1.f;
+        if (a.out_value) a.out_value[gid] = CUDART_NAN_F;
+        if (a.out_logp) a.out_logp[gid] = CUDART_NAN_F;
+        if (a.out_entropy) a.out_entropy[gid] = CUDART_NAN_F;
+      }
+      continue;
+    }
+    const bool big = d.n > NS || 2 * d.e > AS || d.k > KS;
+    if (big) graph_body<TRAIN, true>(a, hd, d, gid, smem, gp, scr);
+    else graph_body<TRAIN, false>(a, hd, d, gid, smem, gp, scr);
+    __syncthreads();
+  }
+}
+
+}  // namespace upb

@@ -1,0 +1,276 @@
+// C-ABI implementation (include/upb200.h): context, launches, optimiser state.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/upb200.h"
+#include "blob.h"
+#include "errors.h"
+#include "layout.h"
+#include "optim_kernels.cuh"
+#include "sgnn_kernel.cuh"
+
+using namespace upb;
+
+struct upb_ctx {
+  upb_config cfg;
+  int num_sms = 0;
+  int grid = 0;
+  float* gpart = nullptr;       // [grid][G_ROW]
+  float* gsum = nullptr;        // [G_ROW]
+  float* scratch = nullptr;     // [grid][scratch_stride]
+  size_t scratch_stride = 0;
+  float* adam_m = nullptr;
+  float* adam_v = nullptr;
+  long long* steps = nullptr;   // device [4]
+  float* host_pinned = nullptr; // [UPB_STAT_COUNT] pinned staging for upb_read_losses
+  int64_t launches = 0;
+};
+
+namespace {
+
+#define UPB_CUDA(call)                                                                       \
+  do {                                                                                       \
+    cudaError_t err__ = (call);                                                              \
+    if (err__ != cudaSuccess) {                                                              \
+      char buf__[512];                                                                       \
+      snprintf(buf__, sizeof(buf__), "%s failed: %s (%s:%d)", #call, cudaGetErrorString(err__), \
+               __FILE__, __LINE__);                                                          \
+      return set_error(UPB_ERR_CUDA, buf__);                                                 \
+    }                                                                                        \
+  } while (0)
+
+struct Slot {
+  const char* name;
+  int offset, rows, cols;
+};
+const Slot kSlots[] = {
+    {"num_w0", P_NUM_W0, 64, 52},      {"num_b0", P_NUM_B0, 64, 0},     {"num_w1", P_NUM_W1, 16, 64},
+    {"num_b1", P_NUM_B1, 16, 0},       {"enc_w", P_ENC_W, 16, 23},      {"enc_b", P_ENC_B, 16, 0},
+    {"gcn0_w", P_GCN0_W, 16, 32},      {"gcn0_b", P_GCN0_B, 16, 0},     {"gcn1_w", P_GCN1_W, 16, 32},
+    {"gcn1_b", P_GCN1_B, 16, 0},       {"mha_in_w", P_MHA_IN_W, 48, 16}, {"mha_in_b", P_MHA_IN_B, 48, 0},
+    {"mha_out_w", P_MHA_OUT_W, 16, 16}, {"mha_out_b", P_MHA_OUT_B, 16, 0}, {"att_q_w", P_ATT_Q_W, 16, 16},
+    {"att_q_b", P_ATT_Q_B, 16, 0},     {"att_k_w", P_ATT_K_W, 16, 16},  {"att_k_b", P_ATT_K_B, 16, 0},
+    {"att_v_w", P_ATT_V_W, 16, 16},    {"att_v_b", P_ATT_V_B, 16, 0},   {"lu_w0", P_LU_W0, 32, 64},
+    {"lu_b0", P_LU_B0, 32, 0},         {"lu_w1", P_LU_W1, 1, 32},       {"road_w0", P_RD_W0, 32, 16},
+    {"road_b0", P_RD_B0, 32, 0},       {"road_w1", P_RD_W1, 1, 32},     {"val_w0", P_VAL_W0, 32, 67},
+    {"val_b0", P_VAL_B0, 32, 0},       {"val_w1", P_VAL_W1, 32, 32},    {"val_b1", P_VAL_B1, 32, 0},
+    {"val_w2", P_VAL_W2, 1, 32},       {"val_b2", P_VAL_B2, 1, 0},
+};
+constexpr int kNumSlots = sizeof(kSlots) / sizeof(kSlots[0]);
+
+int check_ctx(const upb_ctx* ctx, const char* who) {
+  if (!ctx) return set_error(UPB_ERR_ARG, std::string(who) + ": null context");
+  return UPB_OK;
+}
+
+StepArgs base_args(upb_ctx* ctx, const void* blob, const int32_t* ids, int count, const float* params,
+                   const float* actions) {
+  StepArgs a;
+  memset(&a, 0, sizeof(a));
+  a.blob = (const uint8_t*)blob;
+  a.ids = ids;
+  a.count = count;
+  a.params = params;
+  a.actions = actions;
+  a.clip_eps = ctx->cfg.clip_epsilon;
+  a.c_value = ctx->cfg.value_pred_coef;
+  a.c_entropy = ctx->cfg.entropy_coef;
+  a.gpart = ctx->gpart;
+  a.scratch = ctx->scratch;
+  a.scratch_stride = ctx->scratch_stride;
+  a.n_cap = ctx->cfg.n_cap;
+  a.e_cap = ctx->cfg.e_cap;
+  return a;
+}
+
+}  // namespace
+
+extern "C" int upb_num_params(void) { return NUM_PARAMS; }
+
+extern "C" int upb_param_slot(int i, const char** name, int* offset, int* rows, int* cols) {
+  if (i < 0 || i >= kNumSlots) return set_error(UPB_ERR_ARG, "param_slot: index out of range");
+  if (name) *name = kSlots[i].name;
+  if (offset) *offset = kSlots[i].offset;
+  if (rows) *rows = kSlots[i].rows;
+  if (cols) *cols = kSlots[i].cols;
+  return UPB_OK;
+}
+
+extern "C" int upb_create(const upb_config* cfg, upb_ctx** out) {
+  if (!cfg || !out) return set_error(UPB_ERR_ARG, "create: null argument");
+  if (cfg->n_cap < 1 || cfg->n_cap > 65535 || cfg->e_cap < 0 || 2 * (int64_t)cfg->e_cap > 65535)
+    return set_error(UPB_ERR_ARG, "create: caps must satisfy 1 <= n_cap <= 65535 and 2*e_cap <= 65535");
+  if (cfg->clip_mode < 0 || cfg->clip_mode > 2) return set_error(UPB_ERR_ARG, "create: bad clip_mode");
+  UPB_CUDA(cudaSetDevice(cfg->device));
+  cudaDeviceProp prop;
+  UPB_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
+  if (prop.major < 10)
+    return set_error(UPB_ERR_CUDA, "create: this library is built for sm_100a (Blackwell) only");
+  upb_ctx* ctx = new (std::nothrow) upb_ctx();
+  if (!ctx) return set_error(UPB_ERR_ARG, "create: out of host memory");
+  ctx->cfg = *cfg;
+  ctx->num_sms = prop.multiProcessorCount;
+  ctx->grid = ctx->num_sms;
+  if (cfg->grid_limit > 0 && cfg->grid_limit < ctx->grid) ctx->grid = cfg->grid_limit;
+  ctx->scratch_stride = (scratch_floats(cfg->n_cap, cfg->e_cap) + 63) & ~size_t(63);
+  auto fail = [&](int rc) { upb_destroy(ctx); return rc; };
+#define UPB_CUDA_F(call)                                                                     \
+  do {                                                                                       \
+    cudaError_t err__ = (call);                                                              \
+    if (err__ != cudaSuccess) {                                                              \
+      char buf__[512];                                                                       \
+      snprintf(buf__, sizeof(buf__), "%s failed: %s", #call, cudaGetErrorString(err__));     \
+      return fail(set_error(UPB_ERR_CUDA, buf__));                                           \
+    }                                                                                        \
+  } while (0)
+  UPB_CUDA_F(cudaMalloc(&ctx->gpart, sizeof(float) * (size_t)ctx->grid * G_ROW));
+  UPB_CUDA_F(cudaMalloc(&ctx->gsum, sizeof(float) * G_ROW));
+  UPB_CUDA_F(cudaMalloc(&ctx->scratch, sizeof(float) * (size_t)ctx->grid * ctx->scratch_stride));
+  UPB_CUDA_F(cudaMalloc(&ctx->adam_m, sizeof(float) * NUM_PARAMS));
+  UPB_CUDA_F(cudaMalloc(&ctx->adam_v, sizeof(float) * NUM_PARAMS));
+  UPB_CUDA_F(cudaMalloc(&ctx->steps, sizeof(long long) * 4));
+  UPB_CUDA_F(cudaMemset(ctx->adam_m, 0, sizeof(float) * NUM_PARAMS));
+  UPB_CUDA_F(cudaMemset(ctx->adam_v, 0, sizeof(float) * NUM_PARAMS));
+  UPB_CUDA_F(cudaMemset(ctx->steps, 0, sizeof(long long) * 4));
+  UPB_CUDA_F(cudaMemset(ctx->scratch, 0, sizeof(float) * (size_t)ctx->grid * ctx->scratch_stride));
+  UPB_CUDA_F(cudaMallocHost(&ctx->host_pinned, sizeof(float) * UPB_STAT_COUNT));
+  UPB_CUDA_F(cudaFuncSetAttribute(k_sgnn<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+  UPB_CUDA_F(cudaFuncSetAttribute(k_sgnn<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+  UPB_CUDA_F(cudaDeviceSynchronize());
+#undef UPB_CUDA_F
+  *out = ctx;
+  return UPB_OK;
+}
+
+extern "C" void upb_destroy(upb_ctx* ctx) {
+  if (!ctx) return;
+  cudaFree(ctx->gpart);
+  cudaFree(ctx->gsum);
+  cudaFree(ctx->scratch);
+  cudaFree(ctx->adam_m);
+  cudaFree(ctx->adam_v);
+  cudaFree(ctx->steps);
+  if (ctx->host_pinned) cudaFreeHost(ctx->host_pinned);
+  delete ctx;
+}
+
+extern "C" int upb_forward(upb_ctx* ctx, const void* blob_dev, const int32_t* ids, int count, const float* params,
+                           const float* actions, float* value, float* log_prob, float* entropy, int32_t* greedy,
+                           void* stream) {
+  if (int rc = check_ctx(ctx, "forward")) return rc;
+  if (!blob_dev || !params || count < 0) return set_error(UPB_ERR_ARG, "forward: bad argument");
+  if (count == 0) return UPB_OK;
+  StepArgs a = base_args(ctx, blob_dev, ids, count, params, actions);
+  a.out_value = value;
+  a.out_logp = log_prob;
+  a.out_entropy = entropy;
+  a.out_greedy = greedy;
+  const int grid = count < ctx->grid ? count : ctx->grid;
+  k_sgnn<false><<<grid, NT, SMEM_BYTES, (cudaStream_t)stream>>>(a);
+  ctx->launches += 1;
+  UPB_CUDA(cudaGetLastError());
+  return UPB_OK;
+}
+
+extern "C" int upb_ppo_grad(upb_ctx* ctx, const void* blob_dev, const int32_t* ids, int count, const float* params,
+                            const float* actions, const float* advantages, const float* returns,
+                            const float* fixed_log_probs, const float* exps, float inv_batch, float inv_ind,
+                            float* grad_out, void* stream) {
+  if (int rc = check_ctx(ctx, "ppo_grad")) return rc;
+  if (!blob_dev || !params || !actions || !advantages || !returns || !fixed_log_probs || !exps || !grad_out ||
+      count < 0)
+    return set_error(UPB_ERR_ARG, "ppo_grad: bad argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  StepArgs a = base_args(ctx, blob_dev, ids, count, params, actions);
+  a.adv = advantages;
+  a.ret = returns;
+  a.fixed_lp = fixed_log_probs;
+  a.exps = exps;
+  a.inv_batch = inv_batch;
+  a.inv_ind = inv_ind;
+  int grid = count < ctx->grid ? count : ctx->grid;
+  if (grid > 0) {
+    k_sgnn<true><<<grid, NT, SMEM_BYTES, s>>>(a);
+    ctx->launches += 1;
+  }
+  k_reduce_partials<<<(G_ROW + 255) / 256, 256, 0, s>>>(ctx->gpart, grid, ctx->gsum);
+  k_finish_grad<<<1, 256, 0, s>>>(ctx->gsum, params, grad_out);
+  ctx->launches += 2;
+  UPB_CUDA(cudaGetLastError());
+  return UPB_OK;
+}
+
+extern "C" int upb_apply(upb_ctx* ctx, float* params, const float* grad, void* stream) {
+  if (int rc = check_ctx(ctx, "apply")) return rc;
+  if (!params || !grad) return set_error(UPB_ERR_ARG, "apply: bad argument");
+  ApplyArgs a;
+  a.params = params;
+  a.grad = grad;
+  a.m = ctx->adam_m;
+  a.v = ctx->adam_v;
+  a.steps = ctx->steps;
+  a.lr = ctx->cfg.lr;
+  a.beta1 = ctx->cfg.beta1;
+  a.beta2 = ctx->cfg.beta2;
+  a.eps = ctx->cfg.adam_eps;
+  a.clip_mode = ctx->cfg.clip_mode;
+  k_apply<<<1, 1024, 0, (cudaStream_t)stream>>>(a);
+  ctx->launches += 1;
+  UPB_CUDA(cudaGetLastError());
+  return UPB_OK;
+}
+
+extern "C" int upb_read_losses(upb_ctx* ctx, const float* grad, float* out4_host, void* stream) {
+  if (int rc = check_ctx(ctx, "read_losses")) return rc;
+  if (!grad || !out4_host) return set_error(UPB_ERR_ARG, "read_losses: bad argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  UPB_CUDA(cudaMemcpyAsync(ctx->host_pinned, grad + UPB_STAT_OFFSET, sizeof(float) * 8, cudaMemcpyDeviceToHost, s));
+  UPB_CUDA(cudaStreamSynchronize(s));
+  const float* st = ctx->host_pinned;
+  const float nB = st[3] > 0.f ? st[3] : 1.f, nI = st[4] > 0.f ? st[4] : 1.f;
+  const float value_loss = st[0] / nB, surr = st[1] / nI, ent = st[2] / nI;
+  out4_host[0] = surr + ctx->cfg.value_pred_coef * value_loss + ctx->cfg.entropy_coef * ent;
+  out4_host[1] = value_loss;
+  out4_host[2] = surr;
+  out4_host[3] = ent;
+  return UPB_OK;
+}
+
+extern "C" int upb_gae(upb_ctx* ctx, const float* rewards, const float* masks, const float* values, int T,
+                       float gamma, float tau, float* advantages, float* returns, void* stream) {
+  if (int rc = check_ctx(ctx, "gae")) return rc;
+  if (!rewards || !masks || !values || !advantages || !returns || T < 0) return set_error(UPB_ERR_ARG, "gae: bad argument");
+  if (T == 0) return UPB_OK;
+  const float gamma_tau = (float)((double)gamma * (double)tau);
+  k_gae<<<(T + 255) / 256, 256, 0, (cudaStream_t)stream>>>(rewards, masks, values, T, gamma, gamma_tau, advantages,
+                                                           returns);
+  ctx->launches += 1;
+  UPB_CUDA(cudaGetLastError());
+  return UPB_OK;
+}
+
+extern "C" int upb_get_opt_state(upb_ctx* ctx, float* m_host, float* v_host, int64_t* steps4_host) {
+  if (int rc = check_ctx(ctx, "get_opt_state")) return rc;
+  UPB_CUDA(cudaDeviceSynchronize());
+  if (m_host) UPB_CUDA(cudaMemcpy(m_host, ctx->adam_m, sizeof(float) * NUM_PARAMS, cudaMemcpyDeviceToHost));
+  if (v_host) UPB_CUDA(cudaMemcpy(v_host, ctx->adam_v, sizeof(float) * NUM_PARAMS, cudaMemcpyDeviceToHost));
+  if (steps4_host) UPB_CUDA(cudaMemcpy(steps4_host, ctx->steps, sizeof(long long) * 4, cudaMemcpyDeviceToHost));
+  return UPB_OK;
+}
+
+extern "C" int upb_set_opt_state(upb_ctx* ctx, const float* m_host, const float* v_host,
+                                 const int64_t* steps4_host) {
+  if (int rc = check_ctx(ctx, "set_opt_state")) return rc;
+  UPB_CUDA(cudaDeviceSynchronize());
+  if (m_host) UPB_CUDA(cudaMemcpy(ctx->adam_m, m_host, sizeof(float) * NUM_PARAMS, cudaMemcpyHostToDevice));
+  if (v_host) UPB_CUDA(cudaMemcpy(ctx->adam_v, v_host, sizeof(float) * NUM_PARAMS, cudaMemcpyHostToDevice));
+  if (steps4_host) UPB_CUDA(cudaMemcpy(ctx->steps, steps4_host, sizeof(long long) * 4, cudaMemcpyHostToDevice));
+  return UPB_OK;
+}
+
+extern "C" int64_t upb_launch_count(const upb_ctx* ctx) { return ctx ? ctx->launches : 0; }

@@ -1,0 +1,143 @@
+"""Thin Python face of the C ABI: one `Engine` per (process, device).
+
+PyTorch is only the container for device memory and the source of the current CUDA stream; every computation
+of the update path happens inside libupb200.so.  Reference call sites mirrored by the methods are cited in
+include/upb200.h.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from .packing import PackedGraphs
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _f32(t: torch.Tensor, device) -> torch.Tensor:
+    if t.device != device or t.dtype != torch.float32 or not t.is_contiguous():
+        t = t.to(device=device, dtype=torch.float32).contiguous()
+    return t
+
+
+class Engine:
+    def __init__(self, device, n_cap: int, e_cap: int, lr: float = 4e-4, betas=(0.9, 0.999), eps: float = 1e-5,
+                 clip_epsilon: float = 0.2, value_pred_coef: float = 0.5, entropy_coef: float = 0.01,
+                 clip_mode: int = _lib.CLIP_REFERENCE, grid_limit: int = 0, max_graphs: int = 1 << 20):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.UpbError("the update path runs on a CUDA device only (no CPU fallback)")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        cfg = _lib.Config(self.device.index, n_cap, e_cap, max_graphs, lr, betas[0], betas[1], eps,
+                          clip_epsilon, value_pred_coef, entropy_coef, clip_mode, grid_limit)
+        self.cfg = cfg
+        self._ctx = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().upb_create(C.byref(cfg), C.byref(self._ctx)), "upb_create")
+        self.n_cap, self.e_cap = n_cap, e_cap
+
+    def close(self):
+        if getattr(self, "_ctx", None) is not None and self._ctx.value:
+            _lib.lib().upb_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _check_blob(self, blob: PackedGraphs):
+        if blob.n_cap > self.n_cap or blob.e_cap > self.e_cap:
+            raise _lib.UpbError(f"blob caps ({blob.n_cap},{blob.e_cap}) exceed the engine's ({self.n_cap},{self.e_cap})")
+
+    # ------------------------------------------------------------------ no-grad passes
+    def forward(self, blob: PackedGraphs, params: torch.Tensor, actions: Optional[torch.Tensor] = None,
+                ids: Optional[torch.Tensor] = None, want_greedy: bool = False):
+        """value, log_prob, entropy (and greedy action index) per graph of the blob, each shaped (count,).
+        Outputs are indexed by blob position; entries not listed in `ids` are left untouched (zero)."""
+        self._check_blob(blob)
+        n = blob.count
+        dev = self.device
+        value = torch.zeros(n, dtype=torch.float32, device=dev)
+        logp = torch.zeros(n, dtype=torch.float32, device=dev)
+        ent = torch.zeros(n, dtype=torch.float32, device=dev)
+        greedy = torch.zeros(n, dtype=torch.int32, device=dev) if want_greedy else None
+        if actions is not None:
+            actions = _f32(actions, dev)
+            assert actions.numel() == 2 * n, "actions must be (count, 2) like the reference's"
+        cnt = n if ids is None else int(ids.numel())
+        _lib.check(_lib.lib().upb_forward(self._ctx, blob.dev_ptr(), _ptr(ids), cnt, params.data_ptr(),
+                                          _ptr(actions), value.data_ptr(), logp.data_ptr(), ent.data_ptr(),
+                                          _ptr(greedy), self._stream()), "upb_forward")
+        return (value, logp, ent, greedy) if want_greedy else (value, logp, ent)
+
+    # ------------------------------------------------------------------ training step pieces
+    def new_grad_buffer(self) -> torch.Tensor:
+        return torch.zeros(_lib.UPB_GRAD_STRIDE, dtype=torch.float32, device=self.device)
+
+    def ppo_grad(self, blob: PackedGraphs, params: torch.Tensor, actions: torch.Tensor, advantages: torch.Tensor,
+                 returns: torch.Tensor, fixed_log_probs: torch.Tensor, exps: torch.Tensor, inv_batch: float,
+                 inv_ind: float, ids: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None
+                 ) -> torch.Tensor:
+        """Gradient of the PPO loss of the graphs `ids` (all if None) w.r.t. the flat parameters, plus the loss
+        statistics, in one flat buffer (see upb200.h).  Per-sample arrays are indexed by blob position."""
+        self._check_blob(blob)
+        dev = self.device
+        if out is None:
+            out = self.new_grad_buffer()
+        cnt = blob.count if ids is None else int(ids.numel())
+        _lib.check(_lib.lib().upb_ppo_grad(
+            self._ctx, blob.dev_ptr(), _ptr(ids), cnt, params.data_ptr(), _f32(actions, dev).data_ptr(),
+            _f32(advantages, dev).data_ptr(), _f32(returns, dev).data_ptr(), _f32(fixed_log_probs, dev).data_ptr(),
+            _f32(exps, dev).data_ptr(), float(inv_batch), float(inv_ind), out.data_ptr(), self._stream()),
+            "upb_ppo_grad")
+        return out
+
+    def apply(self, params: torch.Tensor, grad: torch.Tensor) -> None:
+        _lib.check(_lib.lib().upb_apply(self._ctx, params.data_ptr(), grad.data_ptr(), self._stream()), "upb_apply")
+
+    def read_losses(self, grad: torch.Tensor) -> Tuple[float, float, float, float]:
+        out = (C.c_float * 4)()
+        _lib.check(_lib.lib().upb_read_losses(self._ctx, grad.data_ptr(), out, self._stream()), "upb_read_losses")
+        return tuple(float(x) for x in out)
+
+    def gae(self, rewards: torch.Tensor, masks: torch.Tensor, values: torch.Tensor, gamma: float, tau: float):
+        dev = self.device
+        r, m, v = _f32(rewards.reshape(-1), dev), _f32(masks.reshape(-1), dev), _f32(values.reshape(-1), dev)
+        T = r.numel()
+        adv = torch.empty(T, dtype=torch.float32, device=dev)
+        ret = torch.empty(T, dtype=torch.float32, device=dev)
+        _lib.check(_lib.lib().upb_gae(self._ctx, r.data_ptr(), m.data_ptr(), v.data_ptr(), T, float(gamma),
+                                      float(tau), adv.data_ptr(), ret.data_ptr(), self._stream()), "upb_gae")
+        return adv, ret
+
+    # ------------------------------------------------------------------ optimiser state
+    def get_opt_state(self):
+        m = np.zeros(_lib.UPB_NUM_PARAMS, np.float32)
+        v = np.zeros(_lib.UPB_NUM_PARAMS, np.float32)
+        steps = np.zeros(4, np.int64)
+        _lib.check(_lib.lib().upb_get_opt_state(self._ctx, m.ctypes.data, v.ctypes.data, steps.ctypes.data),
+                   "upb_get_opt_state")
+        return m, v, steps
+
+    def set_opt_state(self, m: np.ndarray, v: np.ndarray, steps: np.ndarray) -> None:
+        m = np.ascontiguousarray(m, np.float32)
+        v = np.ascontiguousarray(v, np.float32)
+        steps = np.ascontiguousarray(steps, np.int64)
+        _lib.check(_lib.lib().upb_set_opt_state(self._ctx, m.ctypes.data, v.ctypes.data, steps.ctypes.data),
+                   "upb_set_opt_state")
+
+    @property
+    def launches(self) -> int:
+        return int(_lib.lib().upb_launch_count(self._ctx))

@@ -1,0 +1,149 @@
+/*
+ * upb200.h -- C ABI of the B200-native PPO-update path for DRL-urban-planning.
+ *
+ * The reference (tsinghua-fib-lab/DRL-urban-planning) is pure Python and has no FFI; its "operator
+ * interface" for this path is Python duck typing between UrbanPlanningAgent and two nn.Modules
+ * (SURVEY.md section 8(b)).  Every entry point below names the reference call site it replaces.
+ * Conventions: every function returns 0 on success and a negative upb_status otherwise (never aborts,
+ * never throws); upb_last_error() gives the message of the calling thread's last failure.  All tensor
+ * arguments are caller-owned raw pointers (device pointers unless the name says `host`), never freed or
+ * retained past the call.  `stream` is a cudaStream_t passed as void* (0 = legacy default stream).
+ * A context belongs to one (process, device) and is not thread-safe; do not use it in a forked child
+ * (the reference forks rollout workers at khrylib/rl/agents/agent.py:83-89).
+ */
+#ifndef UPB200_H_
+#define UPB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UPB_ABI_VERSION 1
+
+/* model dimensions: fixed by every shipped config (cfg/exp_cfg/.../*.yaml state_encoder_specs,
+ * policy_specs, value_specs); other shapes are rejected by the host layer. */
+#define UPB_NODE_DIM 23
+#define UPB_NODE_STRIDE 24      /* node-feature rows are stored padded to 24 floats (16-byte aligned rows) */
+#define UPB_NUMERICAL_DIM 52
+#define UPB_GCN_DIM 16
+#define UPB_NUM_GCN_LAYERS 2
+#define UPB_NUM_PARAMS 13729
+#define UPB_GRAD_STRIDE 13760   /* flat gradient buffer: 13,729 gradients, 3 pad, then UPB_STAT_COUNT statistics */
+#define UPB_STAT_OFFSET 13732
+#define UPB_STAT_COUNT 28
+/* statistics layout inside the gradient buffer (all sums over the graphs this rank processed, so a
+ * sum-allreduce of the whole buffer yields global values):
+ *   [0] sum (V-R)^2            [1] sum over ind of -min(r A, clip(r) A)   [2] sum over ind of -entropy
+ *   [3] #graphs                [4] #graphs in ind                          [5] #graphs stage land_use
+ *   [6] #graphs stage road     [7] #non-finite per-graph results (NaN guard)            */
+
+typedef enum {
+  UPB_OK = 0,
+  UPB_ERR_ARG = -1,        /* bad argument */
+  UPB_ERR_CUDA = -2,       /* a CUDA call failed */
+  UPB_ERR_FORMAT = -3,     /* a state violates the layout contract (see upb_pack_measure) */
+  UPB_ERR_CAPACITY = -4    /* more graphs / larger graphs than the context was created for */
+} upb_status;
+
+typedef enum {
+  UPB_CLIP_REFERENCE = 0,  /* clip (policy group, then value group, max-norm 1) on the first step of the
+                              context's lifetime only: khrylib/rl/agents/agent_ppo.py:43-46 consumes the two
+                              parameters() generators made at urban_planning_agent.py:46 */
+  UPB_CLIP_ALWAYS = 1,     /* the same two-group clip on every step */
+  UPB_CLIP_NEVER = 2
+} upb_clip_mode;
+
+typedef struct upb_ctx upb_ctx;
+
+typedef struct {
+  int32_t device;          /* CUDA device ordinal */
+  int32_t n_cap, e_cap;    /* largest padded widths (max_num_nodes / max_num_edges of the cfg) */
+  int32_t max_graphs;      /* most graphs one launch may touch */
+  float lr, beta1, beta2, adam_eps;                 /* urban_planning_agent.py:145-149; hlg.yaml:34-36 */
+  float clip_epsilon, value_pred_coef, entropy_coef; /* hlg.yaml:37-39 */
+  int32_t clip_mode;       /* upb_clip_mode */
+  int32_t grid_limit;      /* 0 = one CTA per SM; otherwise cap on CTAs (tests) */
+} upb_config;
+
+/* ---------------------------------------------------------------- library / layout */
+int upb_abi_version(void);
+const char* upb_last_error(void);
+int upb_num_params(void);
+/* i-th tensor of the flat parameter vector, in ActorCritic.parameters() order (models/model.py:36-47).
+ * `name` receives the short name used by drl_urban_planning_b200/params.py. */
+int upb_param_slot(int i, const char** name, int* offset, int* rows, int* cols);
+
+/* ---------------------------------------------------------------- host-side packing (no CUDA)
+ * Replaces tensorfy + SGNNStateEncoder.batch_data (urban_planning_agent.py:16-20,
+ * models/state_encoder.py:163-177): turns `count` states in the reference's padded 9-array layout
+ * (envs/observation_extractor.py:207-228) into one contiguous unpadded blob (DESIGN.md "packed blob").
+ * state_arrays[9*i + j] points at array j of state i:
+ *   0 numerical f32[52]   1 node_features f32[n_cap*23]   2 edge_index i64[e_cap*2]   3 current_node f32[23]
+ *   4 node_mask u8[n_cap] 5 edge_mask u8[e_cap]           6 land_use_mask u8[e_cap]  7 road_mask u8[n_cap]
+ *   8 stage f32[3]
+ * Contract checked here (UPB_ERR_FORMAT otherwise): masks 4/5 are prefix masks, real edges join real nodes,
+ * action masks lie on real edges/nodes, stage is one-hot on 'land_use' or 'road', n >= 1.
+ * upb_pack_measure returns the blob size; upb_pack_fill writes it (blob must be 16-byte aligned).
+ * `threads` <= 0 picks the hardware concurrency. */
+int upb_pack_measure(int count, const void* const* state_arrays, int n_cap, int e_cap, int threads,
+                     uint64_t* blob_bytes);
+int upb_pack_fill(int count, const void* const* state_arrays, int n_cap, int e_cap, int threads,
+                  void* blob_host, uint64_t blob_bytes);
+/* per-graph (n, e, k, stage) of a packed host blob, 4 ints per graph (for tests and load balancing) */
+int upb_blob_info(const void* blob_host, uint64_t blob_bytes, int* count, int32_t* per_graph4);
+
+/* ---------------------------------------------------------------- context */
+int upb_create(const upb_config* cfg, upb_ctx** out);
+void upb_destroy(upb_ctx* ctx);
+
+/* ---------------------------------------------------------------- device path
+ * Per-sample arrays (actions, advantages, returns, fixed_log_probs, exps and all outputs) are indexed by the
+ * graph's position in the blob.  `ids` (device int32[count]) selects the graphs of this call -- a minibatch
+ * is an index list into a resident blob; ids == NULL means graphs 0..count-1. */
+
+/* No-grad pre-passes (urban_planning_agent.py:256-264 value_net(states); :283-292
+ * policy_net.get_log_prob_entropy(states, actions)) and greedy select_action (models/policy.py:67-85,
+ * mean_action=True).  actions: f32[(blob count)*2] as the reference stores them, or NULL (log_prob = 0).
+ * Any output pointer may be NULL. */
+int upb_forward(upb_ctx* ctx, const void* blob_dev, const int32_t* ids, int count, const float* params,
+                const float* actions, float* value, float* log_prob, float* entropy, int32_t* greedy,
+                void* stream);
+
+/* Forward + backward of one (shard of a) minibatch: value_loss + ppo_entropy_loss + loss.backward()
+ * (urban_planning_agent.py:330-335, khrylib/rl/agents/agent_pg.py:19-23).  inv_batch = 1/B and
+ * inv_ind = 1/|ind| are those of the GLOBAL minibatch, so shards on several GPUs sum to the exact batch
+ * gradient.  grad_out: f32[UPB_GRAD_STRIDE] = gradients + statistics (see above), overwritten. */
+int upb_ppo_grad(upb_ctx* ctx, const void* blob_dev, const int32_t* ids, int count, const float* params,
+                 const float* actions, const float* advantages, const float* returns,
+                 const float* fixed_log_probs, const float* exps, float inv_batch, float inv_ind,
+                 float* grad_out, void* stream);
+
+/* clip_policy_grad + optimizer.step (agent_ppo.py:43-46, urban_planning_agent.py:336-337) on the (already
+ * all-reduced) gradient buffer.  Adam moments and step counters live in the context.  A policy head whose
+ * stage count in the statistics is zero is skipped, as torch does for grad None. */
+int upb_apply(upb_ctx* ctx, float* params, const float* grad, void* stream);
+
+/* the 4 scalars the reference logs per minibatch (urban_planning_agent.py:338-345), from a gradient buffer:
+ * out4 = {loss, value_loss, surr_loss, entropy_loss}.  Synchronises `stream`. */
+int upb_read_losses(upb_ctx* ctx, const float* grad, float* out4_host, void* stream);
+
+/* estimate_advantages (khrylib/rl/core/common.py:5-26): rewards f32[T], masks f32[T], values f32[T]
+ * -> advantages f32[T], returns f32[T]; same fp32 operation order as the reference. */
+int upb_gae(upb_ctx* ctx, const float* rewards, const float* masks, const float* values, int T, float gamma,
+            float tau, float* advantages, float* returns, void* stream);
+
+/* optimiser state for checkpoint/resume: m f32[UPB_NUM_PARAMS], v f32[UPB_NUM_PARAMS] (device or host
+ * pointers), steps int64[4] = {global step, encoder+value step, land-use-head step, road-head step}. */
+int upb_get_opt_state(upb_ctx* ctx, float* m_host, float* v_host, int64_t* steps4_host);
+int upb_set_opt_state(upb_ctx* ctx, const float* m_host, const float* v_host, const int64_t* steps4_host);
+
+/* number of kernels this context has launched so far (bench.py "gpu_launches") */
+int64_t upb_launch_count(const upb_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UPB200_H_ */

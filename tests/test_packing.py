@@ -1,0 +1,104 @@
+"""CPU: the host packer (reference 9-array states -> unpadded blob) against a numpy re-derivation, plus the
+layout-contract errors and ragged / edge cases."""
+import numpy as np
+import pytest
+
+from blobview import decode
+from drl_urban_planning_b200 import _lib, synth
+from drl_urban_planning_b200.packing import pack_states
+
+
+def host_bytes(blob):
+    h = blob.host
+    return h.numpy() if hasattr(h, "numpy") else h
+
+
+def check_blob(states, blob):
+    d = decode(host_bytes(blob)[:blob.nbytes])
+    assert d["header"]["count"] == len(states)
+    for i, st in enumerate(states):
+        numerical, nf, ei, cur, nm, em, lum, rm, stage = st
+        g = d["desc"][i]
+        n, e = int(nm.sum()), int(em.sum())
+        assert (g["n"], g["e"]) == (n, e)
+        assert g["stage"] == int(np.argmax(stage[:2]))
+        x = d["x"][g["x_row"]:g["x_row"] + n]
+        assert np.array_equal(x[:, :23], nf[:n]) and not x[:, 23].any()
+        assert np.array_equal(d["num"][i], numerical) and np.array_equal(d["cur"][i][:23], cur)
+        rp = d["rowptr"][g["rp_off"]:g["rp_off"] + n + 1].astype(np.int64)
+        adj = d["adj"][g["adj_off"]:g["adj_off"] + 2 * e]
+        deg = np.bincount(ei[:e, 0], minlength=n) + np.bincount(ei[:e, 1], minlength=n)
+        assert rp[0] == 0 and np.array_equal(np.diff(rp), deg)
+        # the symmetrised adjacency holds every undirected edge exactly twice (once per endpoint)
+        got = sorted((min(i_, int(a & 0xffff)), max(i_, int(a & 0xffff)))
+                     for i_ in range(n) for a in adj[rp[i_]:rp[i_ + 1]])
+        want = sorted((min(int(u), int(v)), max(int(u), int(v))) for u, v in ei[:e] for _ in range(2))
+        assert got == want
+        k = int(g["k"])
+        cuv = d["cuv"][g["cand_off"]:g["cand_off"] + k]
+        cidx = d["cidx"][g["cand_off"]:g["cand_off"] + k]
+        if g["stage"] == 0:
+            idx = np.flatnonzero(lum)
+            assert np.array_equal(cidx, idx)
+            assert np.array_equal(cuv & 0xffff, ei[idx, 0]) and np.array_equal(cuv >> 16, ei[idx, 1])
+            # every directed entry of a candidate edge carries slot+1 in its upper half
+            tagged = {}
+            for i_ in range(n):
+                for a in adj[rp[i_]:rp[i_ + 1]]:
+                    if a >> 16:
+                        tagged.setdefault(int(a >> 16) - 1, []).append((i_, int(a & 0xffff)))
+            assert sorted(tagged) == list(range(k))
+            for s, ends in tagged.items():
+                u, v = int(ei[idx[s], 0]), int(ei[idx[s], 1])
+                assert sorted(ends) == sorted([(u, v), (v, u)])
+        else:
+            idx = np.flatnonzero(rm)
+            assert np.array_equal(cidx, idx) and np.array_equal(cuv, idx)
+            assert not (adj >> 16).any()
+    info = blob.info
+    assert np.array_equal(info[:, 0], [int(s[4].sum()) for s in states])
+
+
+@pytest.mark.parametrize("community,count", [("tiny", 40), ("small", 24), ("hlg", 6), ("hlg_concept", 3)])
+def test_pack_matches_numpy(community, count):
+    states, _ = synth.make_states(5, community, count)
+    for threads in (1, 4):
+        check_blob(states, pack_states(states, threads=threads, pinned=False))
+
+
+def test_pack_edge_cases():
+    spec = synth.COMMUNITIES["tiny"]
+    rng = np.random.default_rng(0)
+    s_one_node, _ = synth.make_state(rng, spec, n=1, stage=1, e=0)          # single node, no edges
+    s_full, _ = synth.make_state(rng, spec, n=spec.max_num_nodes, stage=0)   # node cap reached
+    s_no_cand, _ = synth.make_state(rng, spec, n=10, stage=0)
+    s_no_cand[6][:] = False                                                  # empty action mask
+    s_all_cand, _ = synth.make_state(rng, spec, n=12, stage=0)
+    s_all_cand[6][:int(s_all_cand[5].sum())] = True                          # every real edge is a candidate
+    states = [s_one_node, s_full, s_no_cand, s_all_cand]
+    blob = pack_states(states, pinned=False)
+    check_blob(states, blob)
+    assert blob.info[0].tolist()[:2] == [1, 0] and blob.info[2][2] == 0
+
+
+def test_pack_accepts_torch_and_lists():
+    import torch
+    states, _ = synth.make_states(1, "tiny", 3)
+    as_torch = [[torch.tensor(x) for x in s] for s in states]
+    a = pack_states(states, pinned=False)
+    b = pack_states(as_torch, n_cap=a.n_cap, e_cap=a.e_cap, pinned=False)
+    assert np.array_equal(host_bytes(a)[:a.nbytes], host_bytes(b)[:b.nbytes])
+
+
+@pytest.mark.parametrize("breaker,msg", [
+    (lambda s: s[4].__setitem__(0, False), "prefix"),
+    (lambda s: s[2].__setitem__((0, 0), 47), "padded node"),
+    (lambda s: s[6].__setitem__(159, True), "padded edge"),
+    (lambda s: s[8].__setitem__(slice(None), [0, 0, 1]), "one-hot"),
+])
+def test_pack_rejects_contract_violations(breaker, msg):
+    rng = np.random.default_rng(1)
+    st, _ = synth.make_state(rng, synth.COMMUNITIES["tiny"], n=20, stage=0)
+    breaker(st)
+    with pytest.raises(_lib.UpbError, match=msg):
+        pack_states([st], pinned=False)
