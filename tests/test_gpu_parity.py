@@ -26,11 +26,17 @@ def rel(a, b, floor=1e-9):
 
 
 def per_tensor_rel(ga, gb):
+    """Worst per-tensor max|delta| / max|ref| over the 32 tensors.  Tensors whose gradient is (nearly) a sum of
+    cancelling terms -- attention key biases (exactly zero) and, on tiny batches, head biases (the
+    softmax logit gradients sum to zero) -- are judged against an absolute floor of 1e-7 x the largest gradient
+    entry of the whole model: fp32 cancellation noise, present in the fp32 reference itself."""
+    ga, gb = np.asarray(ga, np.float64), np.asarray(gb, np.float64)
+    floor = 1e-7 * max(np.abs(gb).max(), 1e-9)
     worst, name = 0.0, None
     for s in PL.SLOTS.values():
-        a, b = np.asarray(ga[s.offset:s.offset + s.size], np.float64), np.asarray(gb[s.offset:s.offset + s.size], np.float64)
-        if np.abs(b).max() < 1e-9 and np.abs(a).max() < 1e-7:
-            continue      # mathematically zero gradients: absolute floor
+        a, b = ga[s.offset:s.offset + s.size], gb[s.offset:s.offset + s.size]
+        if np.abs(a - b).max() <= floor:
+            continue
         r = rel(a, b)
         if r > worst:
             worst, name = r, s.name
