@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""PPO-update throughput of the B200 path (BASELINE.json metric: graph-samples/s + achieved HBM GB/s vs roofline).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+A "step" is one PPO minibatch update -- forward + backward of the SGNN policy/value net on 256 rollout graphs per
+GPU, gradient reduction, (N>1: NCCL all-reduce of the 55 KB gradient buffer), clip + Adam -- on synthetic
+HLG-shaped graphs (BASELINE.json configs[1]; SURVEY.md section 8(d) generator, seed 111).  Weak scaling: 256 graphs
+per GPU, global minibatch 256*N.  One JSON line is printed by rank 0; see README/DESIGN.md for the fields.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "ppo_update_graph_samples_per_sec"
+UNIT = "graph-samples/s"
+BATCH = 256
+SEED = 111
+
+
+def read_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                pass
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def make_pool(seed: int, community: str, distinct: int, pool_minibatches: int):
+    """`pool_minibatches` x 256 states: `distinct` generated graphs tiled (duplicates occupy distinct HBM)."""
+    from drl_urban_planning_b200 import synth
+    states, actions = synth.make_states(seed, community, distinct)
+    total = pool_minibatches * BATCH
+    reps = (total + distinct - 1) // distinct
+    order = np.random.default_rng(seed).permutation(distinct * reps)[:total] % distinct
+    return [states[i] for i in order], actions[order]
+
+
+def cpu_port_step_time(states, actions, flat, steps: int, warmup: int, threads: int):
+    """Seconds per PPO minibatch step of the padded eager-PyTorch oracle port (the reference's CPU dataflow)."""
+    import torch
+    from oracle import torch_port as TP
+    torch.set_num_threads(threads)
+    n = len(states)
+    rng = np.random.default_rng(5)
+    adv = torch.tensor(rng.standard_normal((n, 1)).astype(np.float32))
+    ret = torch.tensor(rng.standard_normal((n, 1)).astype(np.float32))
+    fixed = torch.full((n, 1), -4.0)
+    ind = torch.arange(n)
+    agent = TP.PortAgent(flat)
+    act = torch.tensor(actions)
+    times = []
+    for k in range(warmup + steps):
+        t0 = time.perf_counter()
+        b = TP.stack_states(states)                 # tensorfy + batch_data are inside the reference's timed region
+        agent.step(b, act, adv, ret, fixed, ind)
+        if k >= warmup:
+            times.append(time.perf_counter() - t0)
+    return float(np.mean(times))
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU PyTorch dataflow (oracle port; /root/reference is absent on the
+    GPU box and cannot travel) on the host cores, same metric / config."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from drl_urban_planning_b200 import params as PL
+    cores = os.cpu_count() or 1
+    states, actions = make_pool(SEED, args.community, min(args.distinct, BATCH), 1)
+    flat = PL.default_init(SEED)
+    # bounded sample: shrink the per-step sample so the whole run ends within a few minutes
+    probe = cpu_port_step_time(states[:32], actions[:32], flat, 1, 1, cores)
+    per_graph = probe / 32
+    budget = 150.0
+    sample = int(max(16, min(BATCH, budget / max(per_graph * (args.steps + args.warmup), 1e-9))))
+    t = cpu_port_step_time(states[:sample], actions[:sample], flat, args.steps, args.warmup, cores)
+    value = sample / t
+    out = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.community} PPO minibatch update, padded eager PyTorch on CPU (oracle port of the "
+                               f"reference dataflow), {sample} graphs per step", "global_batch": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} steps x {sample} {args.community} graphs, torch threads={cores}"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--community", default="hlg")
+    ap.add_argument("--distinct", type=int, default=512, help="distinct generated graphs per rank (tiled to the pool)")
+    ap.add_argument("--pool", type=int, default=16, help="minibatches resident in HBM (16 x 11.5 MB > 126 MB L2)")
+    ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from drl_urban_planning_b200 import _lib, params as PL
+    from drl_urban_planning_b200.engine import Engine
+    from drl_urban_planning_b200.packing import pack_states
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    # ---- workload: resident pool of minibatches, larger than L2
+    t0 = time.time()
+    states, actions = make_pool(SEED + rank, args.community, args.distinct, args.pool)
+    total = len(states)
+    blob = pack_states(states).to(dev)
+    rng = np.random.default_rng(SEED + 1000 * rank)
+    adv = torch.as_tensor(rng.standard_normal(total).astype(np.float32), device=dev)
+    ret = torch.as_tensor(rng.standard_normal(total).astype(np.float32), device=dev)
+    exps = torch.ones(total, dtype=torch.float32, device=dev)
+    act = torch.as_tensor(actions, device=dev)
+    flat = PL.default_init(SEED)
+    eng = Engine(dev, blob.n_cap, blob.e_cap)
+    params = torch.as_tensor(flat, device=dev).clone()
+    # old log-probs from perturbed weights so that importance ratios straddle the clip range
+    pert = params * (1.0 + 0.05 * torch.randn(params.shape, device=dev, generator=torch.Generator(dev).manual_seed(3)))
+    _, fixed, _ = eng.forward(blob, pert, act)
+    info = blob.info.astype(np.int64)
+    cost = 4 * info[:, 1] + info[:, 0]
+    mb_ids = []
+    for m in range(args.pool):
+        ids = np.arange(m * BATCH, (m + 1) * BATCH)
+        ids = ids[np.argsort(-cost[ids], kind="stable")]        # longest first: static round-robin over CTAs
+        mb_ids.append(torch.as_tensor(ids.astype(np.int32), device=dev))
+    balg_mb = np.array([(1208 * info[m * BATCH:(m + 1) * BATCH, 0] + 42 * info[m * BATCH:(m + 1) * BATCH, 1] + 1300).sum()
+                        for m in range(args.pool)], dtype=np.float64)
+    grad = eng.new_grad_buffer()
+    gB, gI = BATCH * world, BATCH * world
+    setup_s = time.time() - t0
+
+    def step(i):
+        eng.ppo_grad(blob, params, act, adv, ret, fixed, exps, 1.0 / gB, 1.0 / gI, ids=mb_ids[i % args.pool], out=grad)
+        if world > 1:
+            dist.all_reduce(grad, op=dist.ReduceOp.SUM)
+        eng.apply(params, grad)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+        time.sleep(0.15)
+    launches0 = eng.launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for i in range(args.steps):
+        step(args.warmup + i)
+    ev1.record()
+    barrier()
+    ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    total_ms = float(ms.item())
+    launches = eng.launches - launches0
+    clk = clocks.stop() if rank == 0 else None
+    value = BATCH * world * args.steps / (total_ms * 1e-3)
+    losses = eng.read_losses(grad)
+    assert all(np.isfinite(losses)), losses
+
+    # ---- roofline of the dominant kernel (fused SGNN fwd+bwd), CUDA events on the launching stream
+    eng.profile(True)
+    for i in range(args.steps):
+        step(args.warmup + i)
+    kms, kn = eng.profile_read()
+    eng.profile(False)
+    k_avg_ms = kms / max(kn, 1)
+    balg = float(balg_mb[[(args.warmup + i) % args.pool for i in range(args.steps)]].mean())
+    peak, peak_src = read_peaks()
+    achieved = balg / (k_avg_ms * 1e-3) / 1e9
+
+    # ---- end to end: host states (reference layout) -> pack -> H2D -> step -> D2H losses, every step
+    e2e = None
+    if not args.skip_e2e:
+        from drl_urban_planning_b200.packing import pack_states as pk
+        host_adv = torch.as_tensor(rng.standard_normal(BATCH).astype(np.float32)).pin_memory()
+        host_ret = torch.as_tensor(rng.standard_normal(BATCH).astype(np.float32)).pin_memory()
+        host_fix = torch.full((BATCH,), -4.0).pin_memory()
+        host_exp = torch.ones(BATCH).pin_memory()
+        host_buf, dev_buf = None, None
+        n_e2e = max(3, min(args.steps, 20))
+        h2d = 0
+
+        def e2e_step(i):
+            nonlocal host_buf, dev_buf, h2d
+            lo = (i % args.pool) * BATCH
+            b = pk(states[lo:lo + BATCH], blob.n_cap, blob.e_cap, out_host=host_buf)
+            host_buf = b.host
+            b.to(dev, out=dev_buf)
+            dev_buf = b.dev
+            a_h = torch.as_tensor(actions[lo:lo + BATCH]).pin_memory()
+            d = [x.to(dev, non_blocking=True) for x in (a_h, host_adv, host_ret, host_fix, host_exp)]
+            eng.ppo_grad(b, params, d[0], d[1], d[2], d[3], d[4], 1.0 / gB, 1.0 / gI, out=grad)
+            if world > 1:
+                dist.all_reduce(grad, op=dist.ReduceOp.SUM)
+            eng.apply(params, grad)
+            eng.read_losses(grad)                     # D2H of the step's result
+            h2d = b.nbytes + 4 * (BATCH * 2 + BATCH * 4)
+
+        for i in range(2):
+            e2e_step(i)
+        barrier()
+        t1 = time.perf_counter()
+        for i in range(n_e2e):
+            e2e_step(2 + i)
+        barrier()
+        dt = torch.tensor([time.perf_counter() - t1], device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e = {"value": BATCH * world * n_e2e / float(dt.item()), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": 32, "steps": n_e2e,
+               "path": "reference-layout host states -> upb_pack_fill -> pinned -> H2D -> upb_ppo_grad/upb_apply -> D2H losses"}
+
+    # ---- CPU baseline beside it (rank 0, N=1): oracle port of the reference's padded eager dataflow
+    cpu = None
+    if rank == 0 and world == 1 and not args.skip_cpu:
+        cores = os.cpu_count() or 1
+        sample = BATCH
+        tstep = cpu_port_step_time(states[:sample], actions[:sample], flat, 3, 1, cores)
+        cpu = {"value": sample / tstep, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"3 steps (after 1 warm-up) x {sample} {args.community} graphs padded to "
+                         f"{blob.n_cap}/{blob.e_cap}, torch threads={cores}"}
+
+    if rank == 0:
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.community} (cfg {args.community}), PPO minibatch update, {BATCH} rollout graphs per GPU "
+                                   f"per step, caps {blob.n_cap}/{blob.e_cap}, mean n={info[:, 0].mean():.0f} e={info[:, 1].mean():.0f}",
+                       "global_batch": BATCH * world, "parallelism": f"dp{world}",
+                       "l2_policy": f"inputs larger than L2: {args.pool} resident minibatches = {blob.nbytes / 1e6:.0f} MB cycled"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "k_sgnn<TRAIN>", "kernel_ms": k_avg_ms,
+                         "algorithmic_bytes_per_launch": balg, "peak_source": peak_src,
+                         "kernel_share_of_step": k_avg_ms / (total_ms / args.steps)},
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
+            "losses_last_step": [float(x) for x in losses], "setup_s": setup_s,
+        }
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -52,6 +52,8 @@ _PROTOS = {
     "upb_gae": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int, C.c_float, C.c_float, _VP, _VP, _VP]),
     "upb_get_opt_state": (C.c_int, [_VP, _VP, _VP, _VP]),
     "upb_set_opt_state": (C.c_int, [_VP, _VP, _VP, _VP]),
+    "upb_profile_enable": (C.c_int, [_VP, C.c_int]),
+    "upb_profile_read": (C.c_int, [_VP, C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "upb_launch_count": (C.c_int64, [_VP]),
 }
 EXPORTED_SYMBOLS = tuple(_PROTOS)

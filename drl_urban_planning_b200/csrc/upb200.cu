@@ -5,6 +5,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/upb200.h"
@@ -29,6 +30,9 @@ struct upb_ctx {
   long long* steps = nullptr;   // device [4]
   float* host_pinned = nullptr; // [UPB_STAT_COUNT] pinned staging for upb_read_losses
   int64_t launches = 0;
+  bool profiling = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+  size_t prof_used = 0;
 };
 
 namespace {
@@ -66,6 +70,23 @@ constexpr int kNumSlots = sizeof(kSlots) / sizeof(kSlots[0]);
 int check_ctx(const upb_ctx* ctx, const char* who) {
   if (!ctx) return set_error(UPB_ERR_ARG, std::string(who) + ": null context");
   return UPB_OK;
+}
+
+// event pair bracketing the fused kernel while profiling is on (events are pooled and reused)
+bool prof_begin(upb_ctx* ctx, cudaStream_t s) {
+  if (!ctx->profiling) return false;
+  if (ctx->prof_used == ctx->prof_events.size()) {
+    cudaEvent_t a, b;
+    if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return false;
+    ctx->prof_events.emplace_back(a, b);
+  }
+  cudaEventRecord(ctx->prof_events[ctx->prof_used].first, s);
+  return true;
+}
+void prof_end(upb_ctx* ctx, cudaStream_t s, bool on) {
+  if (!on) return;
+  cudaEventRecord(ctx->prof_events[ctx->prof_used].second, s);
+  ctx->prof_used += 1;
 }
 
 StepArgs base_args(upb_ctx* ctx, const void* blob, const int32_t* ids, int count, const float* params,
@@ -156,6 +177,7 @@ extern "C" void upb_destroy(upb_ctx* ctx) {
   cudaFree(ctx->adam_v);
   cudaFree(ctx->steps);
   if (ctx->host_pinned) cudaFreeHost(ctx->host_pinned);
+  for (auto& ev : ctx->prof_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
   delete ctx;
 }
 
@@ -171,7 +193,9 @@ extern "C" int upb_forward(upb_ctx* ctx, const void* blob_dev, const int32_t* id
   a.out_entropy = entropy;
   a.out_greedy = greedy;
   const int grid = count < ctx->grid ? count : ctx->grid;
+  const bool prof = prof_begin(ctx, (cudaStream_t)stream);
   k_sgnn<false><<<grid, NT, SMEM_BYTES, (cudaStream_t)stream>>>(a);
+  prof_end(ctx, (cudaStream_t)stream, prof);
   ctx->launches += 1;
   UPB_CUDA(cudaGetLastError());
   return UPB_OK;
@@ -195,7 +219,9 @@ extern "C" int upb_ppo_grad(upb_ctx* ctx, const void* blob_dev, const int32_t* i
   a.inv_ind = inv_ind;
   int grid = count < ctx->grid ? count : ctx->grid;
   if (grid > 0) {
+    const bool prof = prof_begin(ctx, s);
     k_sgnn<true><<<grid, NT, SMEM_BYTES, s>>>(a);
+    prof_end(ctx, s, prof);
     ctx->launches += 1;
   }
   k_reduce_partials<<<(G_ROW + 255) / 256, 256, 0, s>>>(ctx->gpart, grid, ctx->gsum);
@@ -270,6 +296,27 @@ extern "C" int upb_set_opt_state(upb_ctx* ctx, const float* m_host, const float*
   if (m_host) UPB_CUDA(cudaMemcpy(ctx->adam_m, m_host, sizeof(float) * NUM_PARAMS, cudaMemcpyHostToDevice));
   if (v_host) UPB_CUDA(cudaMemcpy(ctx->adam_v, v_host, sizeof(float) * NUM_PARAMS, cudaMemcpyHostToDevice));
   if (steps4_host) UPB_CUDA(cudaMemcpy(ctx->steps, steps4_host, sizeof(long long) * 4, cudaMemcpyHostToDevice));
+  return UPB_OK;
+}
+
+extern "C" int upb_profile_enable(upb_ctx* ctx, int enable) {
+  if (int rc = check_ctx(ctx, "profile_enable")) return rc;
+  ctx->profiling = enable != 0;
+  return UPB_OK;
+}
+
+extern "C" int upb_profile_read(upb_ctx* ctx, double* total_ms, int* launches) {
+  if (int rc = check_ctx(ctx, "profile_read")) return rc;
+  UPB_CUDA(cudaDeviceSynchronize());
+  double tot = 0.0;
+  for (size_t i = 0; i < ctx->prof_used; ++i) {
+    float ms = 0.f;
+    UPB_CUDA(cudaEventElapsedTime(&ms, ctx->prof_events[i].first, ctx->prof_events[i].second));
+    tot += ms;
+  }
+  if (total_ms) *total_ms = tot;
+  if (launches) *launches = (int)ctx->prof_used;
+  ctx->prof_used = 0;
   return UPB_OK;
 }
 

@@ -138,6 +138,15 @@ class Engine:
         _lib.check(_lib.lib().upb_set_opt_state(self._ctx, m.ctypes.data, v.ctypes.data, steps.ctypes.data),
                    "upb_set_opt_state")
 
+    def profile(self, enable: bool) -> None:
+        _lib.check(_lib.lib().upb_profile_enable(self._ctx, int(enable)), "upb_profile_enable")
+
+    def profile_read(self):
+        """(summed ms of the bracketed fused-kernel launches, number of launches) since the last read."""
+        ms, n = C.c_double(), C.c_int()
+        _lib.check(_lib.lib().upb_profile_read(self._ctx, C.byref(ms), C.byref(n)), "upb_profile_read")
+        return float(ms.value), int(n.value)
+
     @property
     def launches(self) -> int:
         return int(_lib.lib().upb_launch_count(self._ctx))

@@ -1,0 +1,150 @@
+"""PPO update of one training iteration on the B200 path.
+
+Mirrors `UrbanPlanningAgent.update_params` / `update_policy` (reference
+urban_planning/agents/urban_planning_agent.py:248-361) with the same observable behaviour -- values pass, GAE,
+fixed log-probs, `num_optim_epoch` x floor(T/B) minibatch steps on np.random.shuffle permutations, four loss
+scalars per minibatch -- but a different data path:
+
+  * the rollout states are packed ONCE per iteration into an unpadded blob and uploaded with one copy
+    (the reference re-tensorfies every state for each of the 2 + epochs sweeps);
+  * a minibatch is an int32 index list into the resident blob, so a step moves ~1 KB H2D;
+  * one encoder pass yields value, log-prob and entropy (the reference runs the encoder twice per step);
+  * loss scalars stay on the device and are read back once per epoch (the reference syncs 4x per step).
+
+Data parallel: every rank holds the whole buffer, takes `perm[i*B:(i+1)*B][rank::world]` of each global minibatch and
+all-reduces one 55 KB gradient+statistics buffer (NCCL sum) per step; 1/B and 1/|ind| are global, so the summed
+shard gradients equal the single-GPU batch gradient.
+"""
+from __future__ import annotations
+
+import math
+from typing import Callable, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from .engine import Engine
+from .packing import PackedGraphs, pack_states, infer_caps
+
+
+class PPOUpdater:
+    def __init__(self, flat_params, n_cap: int, e_cap: int, device, lr: float = 4e-4, eps: float = 1e-5,
+                 clip_epsilon: float = 0.2, value_pred_coef: float = 0.5, entropy_coef: float = 0.01,
+                 gamma: float = 1.0, tau: float = 0.0, opt_num_epochs: int = 4, mini_batch_size: int = 256,
+                 clip_mode: int = _lib.CLIP_REFERENCE, process_group=None, pack_threads: int = 0):
+        self.device = torch.device(device)
+        self.engine = Engine(self.device, n_cap, e_cap, lr=lr, eps=eps, clip_epsilon=clip_epsilon,
+                             value_pred_coef=value_pred_coef, entropy_coef=entropy_coef, clip_mode=clip_mode)
+        self.device = self.engine.device
+        if isinstance(flat_params, torch.Tensor):
+            self.params = flat_params.detach().to(self.device, torch.float32).contiguous().clone()
+        else:
+            self.params = torch.as_tensor(np.asarray(flat_params, np.float32), device=self.device).clone()
+        assert self.params.numel() == _lib.UPB_NUM_PARAMS
+        self.gamma, self.tau = gamma, tau
+        self.opt_num_epochs, self.mini_batch_size = opt_num_epochs, mini_batch_size
+        self.value_pred_coef, self.entropy_coef = value_pred_coef, entropy_coef
+        self.pack_threads = pack_threads
+        self.pg = process_group
+        self.world, self.rank = 1, 0
+        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            import torch.distributed as dist
+            self.world = dist.get_world_size(process_group)
+            self.rank = dist.get_rank(process_group)
+        self.grad = self.engine.new_grad_buffer()
+        self.blob: Optional[PackedGraphs] = None
+        self._dev_blob_buf = None
+        self.loss_iter = 0
+
+    # ------------------------------------------------------------------ buffer
+    def load_states(self, states: Sequence, actions, exps=None):
+        """Pack + upload the iteration's rollout states (list of reference 9-array states) and their actions."""
+        self.blob = pack_states(states, self.engine.n_cap, self.engine.e_cap, threads=self.pack_threads)
+        self.blob.to(self.device, out=self._dev_blob_buf)
+        self._dev_blob_buf = self.blob.dev
+        T = self.blob.count
+        self.actions = torch.as_tensor(np.ascontiguousarray(actions, np.float32)).reshape(T, 2).to(self.device)
+        e = np.ones(T, np.float32) if exps is None else np.ascontiguousarray(exps, np.float32).reshape(T)
+        self.exps_host = e
+        self.exps = torch.as_tensor(e).to(self.device)
+        return self.blob
+
+    # ------------------------------------------------------------------ pieces of update_params
+    def forward_all(self):
+        """value, log_prob, entropy of every state in the buffer (reference :256-264 and :283-292, one pass)."""
+        return self.engine.forward(self.blob, self.params, self.actions)
+
+    def allreduce(self, buf: torch.Tensor):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.pg)
+
+    def minibatch_step(self, ids: torch.Tensor, global_batch: int, global_ind: int):
+        """One optimiser step on the graphs `ids` (this rank's shard of a global minibatch of `global_batch`
+        graphs, `global_ind` of which have exps != 0): urban_planning_agent.py:322-337."""
+        self.engine.ppo_grad(self.blob, self.params, self.actions, self.advantages, self.returns,
+                             self.fixed_log_probs, self.exps, 1.0 / max(global_batch, 1), 1.0 / max(global_ind, 1),
+                             ids=ids, out=self.grad)
+        self.allreduce(self.grad)
+        self.engine.apply(self.params, self.grad)
+
+    # ------------------------------------------------------------------ the reference's update_params
+    def update_params(self, states: Sequence, actions, rewards, masks, exps=None,
+                      log_fn: Optional[Callable[[str, float, int], None]] = None, iteration: int = 0):
+        """Full update of one iteration.  Returns dict of mean losses per epoch (the reference's 'total_*')."""
+        self.load_states(states, actions, exps)
+        T = self.blob.count
+        dev = self.device
+        values, _, _ = self.forward_all()                                             # :256-264
+        rewards_t = torch.as_tensor(np.ascontiguousarray(rewards, np.float32)).reshape(T).to(dev)
+        masks_t = torch.as_tensor(np.ascontiguousarray(masks, np.float32)).reshape(T).to(dev)
+        self.advantages, self.returns = self.engine.gae(rewards_t, masks_t, values, self.gamma, self.tau)  # :267
+        _, self.fixed_log_probs, _ = self.forward_all()                               # :283-292
+        return self.update_policy(iteration, log_fn)
+
+    def update_policy(self, iteration: int = 0, log_fn=None):
+        T, B = self.blob.count, self.mini_batch_size
+        nb = int(math.floor(T / B))
+        stats_all = torch.zeros(max(nb, 1), 8, dtype=torch.float32, device=self.device)
+        totals = np.zeros(4)
+        for epoch in range(self.opt_num_epochs):
+            perm = np.arange(T)
+            np.random.shuffle(perm)                                                    # :306-307
+            perm_dev = torch.as_tensor(perm.astype(np.int32)).to(self.device)
+            for i in range(nb):
+                sl = slice(i * B, min((i + 1) * B, T))
+                n_ind = int((self.exps_host[perm[sl]] != 0).sum())
+                ids = perm_dev[sl][self.rank::self.world].contiguous()
+                self.minibatch_step(ids, sl.stop - sl.start, n_ind)
+                stats_all[i].copy_(self.grad[_lib.UPB_STAT_OFFSET:_lib.UPB_STAT_OFFSET + 8])
+            st = stats_all[:nb].cpu().numpy().astype(np.float64)                       # one sync per epoch
+            nB, nI = np.maximum(st[:, 3], 1), np.maximum(st[:, 4], 1)
+            vl, sl_, el = st[:, 0] / nB, st[:, 1] / nI, st[:, 2] / nI
+            loss = sl_ + self.value_pred_coef * vl + self.entropy_coef * el
+            if st[:, 7].any():
+                raise FloatingPointError("non-finite value / log-prob / entropy in the PPO update")
+            if log_fn is not None:
+                for i in range(nb):
+                    log_fn("loss/loss", float(loss[i]), self.loss_iter + i)
+                    log_fn("loss/value_loss", float(vl[i]), self.loss_iter + i)
+                    log_fn("loss/surr_loss", float(sl_[i]), self.loss_iter + i)
+                    log_fn("loss/entropy_loss", float(el[i]), self.loss_iter + i)
+                ge = iteration * self.opt_num_epochs + epoch
+                log_fn("loss/epoch_loss", float(loss.sum()), ge)
+                log_fn("loss/epoch_value_loss", float(vl.sum()), ge)
+                log_fn("loss/epoch_surr_loss", float(sl_.sum()), ge)
+                log_fn("loss/epoch_entropy_loss", float(el.sum()), ge)
+            self.loss_iter += nb
+            totals += [loss.sum(), vl.sum(), sl_.sum(), el.sum()]
+        totals /= max(self.opt_num_epochs, 1)
+        if log_fn is not None:
+            log_fn("loss/total_loss", float(totals[0]), iteration)
+            log_fn("loss/total_value_loss", float(totals[1]), iteration)
+            log_fn("loss/total_surr_loss", float(totals[2]), iteration)
+            log_fn("loss/total_entropy_loss", float(totals[3]), iteration)
+        return dict(total_loss=totals[0], total_value_loss=totals[1], total_surr_loss=totals[2],
+                    total_entropy_loss=totals[3])
+
+    def flat_params(self) -> np.ndarray:
+        return self.params.detach().cpu().numpy()

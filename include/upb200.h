@@ -140,6 +140,12 @@ int upb_gae(upb_ctx* ctx, const float* rewards, const float* masks, const float*
 int upb_get_opt_state(upb_ctx* ctx, float* m_host, float* v_host, int64_t* steps4_host);
 int upb_set_opt_state(upb_ctx* ctx, const float* m_host, const float* v_host, const int64_t* steps4_host);
 
+/* Kernel timing for the roofline line of bench.py: while enabled, upb_ppo_grad / upb_forward bracket the fused
+ * SGNN kernel with CUDA events on the launching stream.  upb_profile_read synchronises the device and returns the
+ * summed duration (ms) and the number of bracketed launches since the last read. */
+int upb_profile_enable(upb_ctx* ctx, int enable);
+int upb_profile_read(upb_ctx* ctx, double* total_ms, int* launches);
+
 /* number of kernels this context has launched so far (bench.py "gpu_launches") */
 int64_t upb_launch_count(const upb_ctx* ctx);
 
