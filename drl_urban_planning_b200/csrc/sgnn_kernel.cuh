@@ -58,7 +58,9 @@ constexpr int S_RDW0 = S_LUW1 + 32;        // [32][16]
 constexpr int S_RDW0T = S_RDW0 + 512;      // [16][32]
 constexpr int S_RDB0 = S_RDW0T + 512;      // [32]
 constexpr int S_RDW1 = S_RDB0 + 32;        // [32]
-constexpr int S_WEND = S_RDW1 + 32;
+constexpr int S_WPQT0 = S_RDW1 + 32;       // [16][32]  transpose of S_WPQ0 (bank-conflict-free EPQ phase)
+constexpr int S_WPQT1 = S_WPQT0 + 512;
+constexpr int S_WEND = S_WPQT1 + 512;
 
 // per-graph small vectors
 constexpr int V_X52 = 0;        // [52] numerical features (padded to 56)
@@ -257,6 +259,8 @@ __device__ __forceinline__ void load_weights(const float* __restrict__ P, float*
     const int src = o < 16 ? o * 32 + c : (o - 16) * 32 + 16 + c;
     sW[S_WPQ0 + i] = P[P_GCN0_W + src];
     sW[S_WPQ1 + i] = P[P_GCN1_W + src];
+    sW[S_WPQT0 + c * 32 + o] = P[P_GCN0_W + src];
+    sW[S_WPQT1 + c * 32 + o] = P[P_GCN1_W + src];
   }
   if (t < 16) {
     sW[S_B0 + t] = P[P_GCN0_B + t];
@@ -320,25 +324,32 @@ struct GraphView {
   const int* cidx;         // [k]
 };
 
-// exp-transformed edge-MLP pre-activations of one layer: EPQ[i][o] = exp(2 (Wpq[o] . h_i + b[o]))  (b only for o<16)
-__device__ __forceinline__ void epq_phase(const GraphView& g, const float* hsrc, const float* Wpq, const float* b) {
-  for (int task = threadIdx.x; task < g.n * 8; task += NT) {
-    const int i = task >> 3, og = task & 7;
-    const float4 h0 = ld4(hsrc + i * 16), h1 = ld4(hsrc + i * 16 + 4), h2 = ld4(hsrc + i * 16 + 8),
-                 h3 = ld4(hsrc + i * 16 + 12);
-    float out[4];
+// exp-transformed edge-MLP pre-activations of one layer: EPQ[i][o] = exp(2 (Wpq[o] . h_i + b[o]))  (b only for o<16).
+// 8 lanes per node PAIR, 4 outputs per lane; WT is the [16 c][32 o] transpose so a quarter-warp reads 128
+// contiguous bytes (no bank conflicts) and every weight vector is reused for two nodes.
+__device__ __forceinline__ void epq_phase(const GraphView& g, const float* hsrc, const float* WT, const float* b) {
+  const int og = threadIdx.x & 7;
+  const float4 bias = og < 4 ? ld4(b + og * 4) : f4(0.f);
+  const int npair = (g.n + 1) >> 1;
+  for (int task = threadIdx.x; task < npair * 8; task += NT) {
+    const int i0 = (task >> 3) * 2;
+    const int i1 = min(i0 + 1, g.n - 1);
+    float ha[16], hb[16];
 #pragma unroll
-    for (int oo = 0; oo < 4; ++oo) {
-      const int o = og * 4 + oo;
-      const float* w = Wpq + o * 16;
-      float s = o < 16 ? b[o] : 0.f;
-      s += dot4(ld4(w), h0);
-      s += dot4(ld4(w + 4), h1);
-      s += dot4(ld4(w + 8), h2);
-      s += dot4(ld4(w + 12), h3);
-      out[oo] = exp2a(s);
+    for (int j = 0; j < 4; ++j) {
+      const float4 a = ld4(hsrc + i0 * 16 + j * 4), c = ld4(hsrc + i1 * 16 + j * 4);
+      ha[j * 4] = a.x; ha[j * 4 + 1] = a.y; ha[j * 4 + 2] = a.z; ha[j * 4 + 3] = a.w;
+      hb[j * 4] = c.x; hb[j * 4 + 1] = c.y; hb[j * 4 + 2] = c.z; hb[j * 4 + 3] = c.w;
     }
-    st4(g.EPQ + i * 32 + og * 4, make_float4(out[0], out[1], out[2], out[3]));
+    float4 sa = bias, sb = bias;
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      const float4 w = ld4(WT + c * 32 + og * 4);
+      sa.x = fmaf(w.x, ha[c], sa.x); sa.y = fmaf(w.y, ha[c], sa.y); sa.z = fmaf(w.z, ha[c], sa.z); sa.w = fmaf(w.w, ha[c], sa.w);
+      sb.x = fmaf(w.x, hb[c], sb.x); sb.y = fmaf(w.y, hb[c], sb.y); sb.z = fmaf(w.z, hb[c], sb.z); sb.w = fmaf(w.w, hb[c], sb.w);
+    }
+    st4(g.EPQ + i0 * 32 + og * 4, make_float4(exp2a(sa.x), exp2a(sa.y), exp2a(sa.z), exp2a(sa.w)));
+    if (i1 != i0) st4(g.EPQ + i1 * 32 + og * 4, make_float4(exp2a(sb.x), exp2a(sb.y), exp2a(sb.z), exp2a(sb.w)));
   }
 }
 
@@ -462,7 +473,7 @@ __device__ void graph_body(const StepArgs& a, const BlobHeader& hd, const GraphD
 
   // GCN layers (state_encoder.py:194-197): h <- h + (sum_{nbr} he) / (deg + eps), pull over the CSR
   for (int l = 0; l < 2; ++l) {
-    epq_phase(g, g.H, sW + (l == 0 ? S_WPQ0 : S_WPQ1), sW + (l == 0 ? S_B0 : S_B1));
+    epq_phase(g, g.H, sW + (l == 0 ? S_WPQT0 : S_WPQT1), sW + (l == 0 ? S_B0 : S_B1));
     __syncthreads();
     float4 msum = f4(0.f), hsum = f4(0.f);
     for (int task = tid; task < n * 4; task += NT) {
@@ -470,13 +481,23 @@ __device__ void graph_body(const StepArgs& a, const BlobHeader& hd, const GraphD
       const float4 epi = ld4(g.EPQ + i * 32 + q * 4), eqi = ld4(g.EPQ + i * 32 + 16 + q * 4);
       const int beg = g.rp[i], end = g.rp[i + 1];
       float4 acc = f4(0.f);
-      for (int t = beg; t < end; ++t) {
-        const int kk = g.adj[t] & 0xffffu;
-        const float4 epk = ld4(g.EPQ + kk * 32 + q * 4), eqk = ld4(g.EPQ + kk * 32 + 16 + q * 4);
-        acc.x += (1.f - rcp_approx(fmaf(epi.x, eqk.x, 1.f))) - rcp_approx(fmaf(epk.x, eqi.x, 1.f));
-        acc.y += (1.f - rcp_approx(fmaf(epi.y, eqk.y, 1.f))) - rcp_approx(fmaf(epk.y, eqi.y, 1.f));
-        acc.z += (1.f - rcp_approx(fmaf(epi.z, eqk.z, 1.f))) - rcp_approx(fmaf(epk.z, eqi.z, 1.f));
-        acc.w += (1.f - rcp_approx(fmaf(epi.w, eqk.w, 1.f))) - rcp_approx(fmaf(epk.w, eqi.w, 1.f));
+      for (int t = beg; t < end; t += 2) {       // two neighbours per trip for memory-level parallelism
+        const bool two = t + 1 < end;
+        const int k0 = g.adj[t] & 0xffffu;
+        const int k1 = two ? (int)(g.adj[t + 1] & 0xffffu) : k0;
+        const float4 ep0 = ld4(g.EPQ + k0 * 32 + q * 4), eq0 = ld4(g.EPQ + k0 * 32 + 16 + q * 4);
+        const float4 ep1 = ld4(g.EPQ + k1 * 32 + q * 4), eq1 = ld4(g.EPQ + k1 * 32 + 16 + q * 4);
+        float4 c0, c1;
+        c0.x = (1.f - rcp_approx(fmaf(epi.x, eq0.x, 1.f))) - rcp_approx(fmaf(ep0.x, eqi.x, 1.f));
+        c0.y = (1.f - rcp_approx(fmaf(epi.y, eq0.y, 1.f))) - rcp_approx(fmaf(ep0.y, eqi.y, 1.f));
+        c0.z = (1.f - rcp_approx(fmaf(epi.z, eq0.z, 1.f))) - rcp_approx(fmaf(ep0.z, eqi.z, 1.f));
+        c0.w = (1.f - rcp_approx(fmaf(epi.w, eq0.w, 1.f))) - rcp_approx(fmaf(ep0.w, eqi.w, 1.f));
+        c1.x = (1.f - rcp_approx(fmaf(epi.x, eq1.x, 1.f))) - rcp_approx(fmaf(ep1.x, eqi.x, 1.f));
+        c1.y = (1.f - rcp_approx(fmaf(epi.y, eq1.y, 1.f))) - rcp_approx(fmaf(ep1.y, eqi.y, 1.f));
+        c1.z = (1.f - rcp_approx(fmaf(epi.z, eq1.z, 1.f))) - rcp_approx(fmaf(ep1.z, eqi.z, 1.f));
+        c1.w = (1.f - rcp_approx(fmaf(epi.w, eq1.w, 1.f))) - rcp_approx(fmaf(ep1.w, eqi.w, 1.f));
+        acc = acc + c0;
+        if (two) acc = acc + c1;
       }
       const float iv = g.inv[i];
       float4 h = ld4(g.H + i * 16 + q * 4);
@@ -867,7 +888,7 @@ __device__ void graph_body(const StepArgs& a, const BlobHeader& hd, const GraphD
     const float* Wpq = sW + (l == 0 ? S_WPQ0 : S_WPQ1);
     const float* hin = l == 0 ? g.H0g : g.H1g;     // layer input h^l (global scratch)
     if (l == 0) {   // EPQ of layer 0 was overwritten by layer 1: recompute from h^0
-      epq_phase(g, hin, Wpq, sW + S_B0);
+      epq_phase(g, hin, sW + S_WPQT0, sW + S_B0);
       __syncthreads();
     }
     const bool last = (l == 1);
@@ -880,22 +901,32 @@ __device__ void graph_body(const StepArgs& a, const BlobHeader& hd, const GraphD
       const float4 gsi = ld4(g.H + i * 16 + q * 4) * g.inv[i] + ce4;
       const int beg = g.rp[i], end = g.rp[i + 1];
       float4 aP = f4(0.f), aQ = f4(0.f);
-      for (int t = beg; t < end; ++t) {
-        const uint32_t ent = g.adj[t];
-        const int kk = ent & 0xffffu;
-        const float4 epk = ld4(g.EPQ + kk * 32 + q * 4), eqk = ld4(g.EPQ + kk * 32 + 16 + q * 4);
-        float4 ge = gsi + ld4(g.H + kk * 16 + q * 4) * g.inv[kk];
-        if (use_head && (ent >> 16)) ge = ge + ld4(g.ghead + (size_t)((ent >> 16) - 1) * 16 + q * 4);
+      for (int t = beg; t < end; t += 2) {
+        const bool two = t + 1 < end;
+        const uint32_t ent0 = g.adj[t];
+        const uint32_t ent1 = two ? g.adj[t + 1] : ent0;
+        const int k0 = ent0 & 0xffffu, k1 = ent1 & 0xffffu;
+        const float4 ep0 = ld4(g.EPQ + k0 * 32 + q * 4), eq0 = ld4(g.EPQ + k0 * 32 + 16 + q * 4);
+        const float4 ep1 = ld4(g.EPQ + k1 * 32 + q * 4), eq1 = ld4(g.EPQ + k1 * 32 + 16 + q * 4);
+        float4 ge0 = gsi + ld4(g.H + k0 * 16 + q * 4) * g.inv[k0];
+        float4 ge1 = gsi + ld4(g.H + k1 * 16 + q * 4) * g.inv[k1];
+        if (use_head) {
+          if (ent0 >> 16) ge0 = ge0 + ld4(g.ghead + (size_t)((ent0 >> 16) - 1) * 16 + q * 4);
+          if (ent1 >> 16) ge1 = ge1 + ld4(g.ghead + (size_t)((ent1 >> 16) - 1) * 16 + q * 4);
+        }
+        if (!two) ge1 = f4(0.f);
         float r;
         // d tanh = 1 - t^2 = 4 r (1 - r);  g1 = ge/2 * (1 - t1^2) = 2 ge r1 (1 - r1)
-        r = rcp_approx(fmaf(epi.x, eqk.x, 1.f)); aP.x = fmaf(ge.x, 2.f * r * (1.f - r), aP.x);
-        r = rcp_approx(fmaf(epi.y, eqk.y, 1.f)); aP.y = fmaf(ge.y, 2.f * r * (1.f - r), aP.y);
-        r = rcp_approx(fmaf(epi.z, eqk.z, 1.f)); aP.z = fmaf(ge.z, 2.f * r * (1.f - r), aP.z);
-        r = rcp_approx(fmaf(epi.w, eqk.w, 1.f)); aP.w = fmaf(ge.w, 2.f * r * (1.f - r), aP.w);
-        r = rcp_approx(fmaf(epk.x, eqi.x, 1.f)); aQ.x = fmaf(ge.x, 2.f * r * (1.f - r), aQ.x);
-        r = rcp_approx(fmaf(epk.y, eqi.y, 1.f)); aQ.y = fmaf(ge.y, 2.f * r * (1.f - r), aQ.y);
-        r = rcp_approx(fmaf(epk.z, eqi.z, 1.f)); aQ.z = fmaf(ge.z, 2.f * r * (1.f - r), aQ.z);
-        r = rcp_approx(fmaf(epk.w, eqi.w, 1.f)); aQ.w = fmaf(ge.w, 2.f * r * (1.f - r), aQ.w);
+#define UPB_BWD_TERM(EA, EB, GE, ACC) r = rcp_approx(fmaf(EA, EB, 1.f)); ACC = fmaf(GE, 2.f * r * (1.f - r), ACC);
+        UPB_BWD_TERM(epi.x, eq0.x, ge0.x, aP.x) UPB_BWD_TERM(epi.y, eq0.y, ge0.y, aP.y)
+        UPB_BWD_TERM(epi.z, eq0.z, ge0.z, aP.z) UPB_BWD_TERM(epi.w, eq0.w, ge0.w, aP.w)
+        UPB_BWD_TERM(ep0.x, eqi.x, ge0.x, aQ.x) UPB_BWD_TERM(ep0.y, eqi.y, ge0.y, aQ.y)
+        UPB_BWD_TERM(ep0.z, eqi.z, ge0.z, aQ.z) UPB_BWD_TERM(ep0.w, eqi.w, ge0.w, aQ.w)
+        UPB_BWD_TERM(epi.x, eq1.x, ge1.x, aP.x) UPB_BWD_TERM(epi.y, eq1.y, ge1.y, aP.y)
+        UPB_BWD_TERM(epi.z, eq1.z, ge1.z, aP.z) UPB_BWD_TERM(epi.w, eq1.w, ge1.w, aP.w)
+        UPB_BWD_TERM(ep1.x, eqi.x, ge1.x, aQ.x) UPB_BWD_TERM(ep1.y, eqi.y, ge1.y, aQ.y)
+        UPB_BWD_TERM(ep1.z, eqi.z, ge1.z, aQ.z) UPB_BWD_TERM(ep1.w, eqi.w, ge1.w, aQ.w)
+#undef UPB_BWD_TERM
       }
       st4(g.GPQ + i * 32 + q * 4, aP);
       st4(g.GPQ + i * 32 + 16 + q * 4, aQ);
