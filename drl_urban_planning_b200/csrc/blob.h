@@ -10,6 +10,7 @@
 //   float      numerical[count][52]
 //   float      cur[count][24]        current-node features, padded
 //   uint16     rowptr[...]           per graph n+1 entries (CSR over the symmetrised adjacency), padded to 8
+//   uint16     order[...]            per graph n node ids by descending degree (same per-graph offsets as rowptr)
 //   uint32     adj[...]              per graph 2e directed entries: neighbour | (slot+1) << 16, padded to 4
 //                                    slot = rank of the entry's undirected edge among the land-use candidates
 //   uint32     cand_uv[...]          per graph k candidates of the active stage: u | v << 16 (edges) or node id
@@ -30,7 +31,8 @@ struct BlobHeader {
   uint64_t total_bytes;
   uint64_t off_desc, off_x, off_num, off_cur, off_rowptr, off_adj, off_cand_uv, off_cand_idx;
   uint64_t sum_n, sum_e, sum_k;
-  uint64_t reserved[2];
+  uint64_t off_order;   // uint16: per graph n node ids sorted by descending degree, at the graph's rp_off
+  uint64_t reserved[1];
 };
 static_assert(sizeof(BlobHeader) == 128, "BlobHeader must be 128 bytes");
 

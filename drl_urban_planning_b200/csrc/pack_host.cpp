@@ -167,6 +167,7 @@ int make_plan(int count, const void* const* arrays, int n_cap, int e_cap, int th
   h.off_num = off;       off = align16(off + (uint64_t)count * kNumDim * sizeof(float));
   h.off_cur = off;       off = align16(off + (uint64_t)count * kNodeStride * sizeof(float));
   h.off_rowptr = off;    off = align16(off + rp * sizeof(uint16_t));
+  h.off_order = off;     off = align16(off + rp * sizeof(uint16_t));
   h.off_adj = off;       off = align16(off + adj * sizeof(uint32_t));
   h.off_cand_uv = off;   off = align16(off + cand * sizeof(uint32_t));
   h.off_cand_idx = off;  off = align16(off + cand * sizeof(int32_t));
@@ -199,6 +200,14 @@ void fill_one(const StateView& s, const GraphDesc& d, const BlobHeader& h, uint8
   for (int i = 0; i < n; ++i) pos[i + 1] += pos[i];
   for (int i = 0; i <= n; ++i) rp[i] = (uint16_t)pos[i];
   for (int i = n + 1; i < ((n + 1 + 7) & ~7); ++i) rp[i] = (uint16_t)pos[n];
+  {  // nodes by descending degree (stable): a warp's 8 nodes then share almost the same trip count in the pull
+    uint16_t* ord = (uint16_t*)(blob + h.off_order) + d.rp_off;
+    std::vector<int> idx(n);
+    for (int i = 0; i < n; ++i) idx[i] = i;
+    std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return pos[a + 1] - pos[a] > pos[b + 1] - pos[b]; });
+    for (int i = 0; i < n; ++i) ord[i] = (uint16_t)idx[i];
+    for (int i = n; i < ((n + 1 + 7) & ~7); ++i) ord[i] = 0;
+  }
   int slot = 0;
   for (int j = 0; j < e; ++j) {
     const uint32_t u = (uint32_t)s.edge_index[2 * j], v = (uint32_t)s.edge_index[2 * j + 1];

@@ -109,7 +109,8 @@ constexpr int S_GHEAD = S_GZ + KS;               // [KS][16]
 constexpr int S_CUV = S_GHEAD + KS * 16;         // [KS] u32
 constexpr int S_CIDX = S_CUV + KS;               // [KS] i32
 constexpr int S_RP = S_CIDX + KS;                // [(NS+8)/2] u16 pairs
-constexpr int S_ADJ = S_RP + (NS + 8) / 2;       // [AS] u32
+constexpr int S_ORD = S_RP + (NS + 8) / 2;       // [(NS+8)/2] u16 pairs: nodes by descending degree
+constexpr int S_ADJ = S_ORD + (NS + 8) / 2;      // [AS] u32
 constexpr int S_EPQ = S_ADJ + AS;                // [NS][32]
 constexpr int S_GPQ = S_EPQ + NS * 32;           // [NS][32]   (aliased by the head-backward chunk buffers)
 constexpr int S_H = S_GPQ + NS * 32;             // [NS][16]
@@ -171,6 +172,41 @@ __device__ __forceinline__ float4 operator*(float4 a, float s) { return make_flo
 __device__ __forceinline__ float4 operator*(float4 a, float4 b) { return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w); }
 __device__ __forceinline__ float dot4(float4 a, float4 b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
 __device__ __forceinline__ float comp(const float4& v, int j) { return j == 0 ? v.x : j == 1 ? v.y : j == 2 ? v.z : v.w; }
+
+// packed fp32 pairs (FFMA2 / FMUL2 / FADD2 on sm_100a): channels (x,y) and (z,w) of a float4
+struct F2x2 { float2 a, b; };
+__device__ __forceinline__ F2x2 ldp(const float* p) {
+  const float4 v = ld4(p);
+  F2x2 r; r.a = make_float2(v.x, v.y); r.b = make_float2(v.z, v.w);
+  return r;
+}
+__device__ __forceinline__ float2 rcp2(float2 v) { return make_float2(rcp_approx(v.x), rcp_approx(v.y)); }
+__device__ __forceinline__ float2 neg2(float2 v) { return make_float2(-v.x, -v.y); }
+
+// Forward message of one directed entry, two channels: accumulates r1 + r2 into s, where
+//   r1 = 1/(EP_i EQ_k + 1), r2 = 1/(EP_k EQ_i + 1),  he = 1 - r1 - r2.
+// Fast form: r1 + r2 = (a + b) / (a b) -> ONE reciprocal per channel; valid while a b cannot overflow, which the
+// EPQ phase guarantees by flagging graphs with |pre-activation| > 10.9 (then EXACT = two reciprocals is used).
+template <bool EXACT>
+__device__ __forceinline__ void fwd_term(float2 epi, float2 eqi, float2 epk, float2 eqk, float2& s) {
+  const float2 one = make_float2(1.f, 1.f);
+  const float2 a = __ffma2_rn(epi, eqk, one), b = __ffma2_rn(epk, eqi, one);
+  if (EXACT) s = __fadd2_rn(s, __fadd2_rn(rcp2(a), rcp2(b)));
+  else s = __ffma2_rn(__fadd2_rn(a, b), rcp2(__fmul2_rn(a, b)), s);
+}
+// Backward of the same entry: aP += ge2 r1 (1 - r1), aQ += ge2 r2 (1 - r2) with ge2 = 2 g_he
+// (1 - tanh^2 = 4 r (1 - r) and g1 = g_he/2 (1 - t1^2)).
+template <bool EXACT>
+__device__ __forceinline__ void bwd_term(float2 epi, float2 eqi, float2 epk, float2 eqk, float2 ge2, float2& aP,
+                                         float2& aQ) {
+  const float2 one = make_float2(1.f, 1.f);
+  const float2 a = __ffma2_rn(epi, eqk, one), b = __ffma2_rn(epk, eqi, one);
+  float2 r1, r2;
+  if (EXACT) { r1 = rcp2(a); r2 = rcp2(b); }
+  else { const float2 R = rcp2(__fmul2_rn(a, b)); r1 = __fmul2_rn(b, R); r2 = __fmul2_rn(a, R); }
+  aP = __ffma2_rn(ge2, __fmul2_rn(r1, __fadd2_rn(one, neg2(r1))), aP);
+  aQ = __ffma2_rn(ge2, __fmul2_rn(r2, __fadd2_rn(one, neg2(r2))), aQ);
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -319,6 +355,7 @@ struct GraphView {
   float* gz;               // [k]
   float* ghead;            // [k][16]
   const uint16_t* rp;      // [n+1]
+  const uint16_t* ord;     // [n] node ids by descending degree (warp-uniform trip counts in the pull)
   const uint32_t* adj;     // [2e]
   const uint32_t* cuv;     // [k]
   const int* cidx;         // [k]
@@ -327,10 +364,11 @@ struct GraphView {
 // exp-transformed edge-MLP pre-activations of one layer: EPQ[i][o] = exp(2 (Wpq[o] . h_i + b[o]))  (b only for o<16).
 // 8 lanes per node PAIR, 4 outputs per lane; WT is the [16 c][32 o] transpose so a quarter-warp reads 128
 // contiguous bytes (no bank conflicts) and every weight vector is reused for two nodes.
-__device__ __forceinline__ void epq_phase(const GraphView& g, const float* hsrc, const float* WT, const float* b) {
+__device__ __forceinline__ int epq_phase(const GraphView& g, const float* hsrc, const float* WT, const float* b) {
   const int og = threadIdx.x & 7;
   const float4 bias = og < 4 ? ld4(b + og * 4) : f4(0.f);
   const int npair = (g.n + 1) >> 1;
+  float amax = 0.f;
   for (int task = threadIdx.x; task < npair * 8; task += NT) {
     const int i0 = (task >> 3) * 2;
     const int i1 = min(i0 + 1, g.n - 1);
@@ -348,9 +386,85 @@ __device__ __forceinline__ void epq_phase(const GraphView& g, const float* hsrc,
       sa.x = fmaf(w.x, ha[c], sa.x); sa.y = fmaf(w.y, ha[c], sa.y); sa.z = fmaf(w.z, ha[c], sa.z); sa.w = fmaf(w.w, ha[c], sa.w);
       sb.x = fmaf(w.x, hb[c], sb.x); sb.y = fmaf(w.y, hb[c], sb.y); sb.z = fmaf(w.z, hb[c], sb.z); sb.w = fmaf(w.w, hb[c], sb.w);
     }
+    amax = fmaxf(amax, fmaxf(fmaxf(fabsf(sa.x), fabsf(sa.y)), fmaxf(fabsf(sa.z), fabsf(sa.w))));
+    amax = fmaxf(amax, fmaxf(fmaxf(fabsf(sb.x), fabsf(sb.y)), fmaxf(fabsf(sb.z), fabsf(sb.w))));
     st4(g.EPQ + i0 * 32 + og * 4, make_float4(exp2a(sa.x), exp2a(sa.y), exp2a(sa.z), exp2a(sa.w)));
     if (i1 != i0) st4(g.EPQ + i1 * 32 + og * 4, make_float4(exp2a(sb.x), exp2a(sb.y), exp2a(sb.z), exp2a(sb.w)));
   }
+  return !(amax <= 10.9f);      // also true for NaN
+}
+
+// one GCN layer forward, in place: H[i] += (sum over the CSR row of he(i,k)) / (deg_i + eps).  4 lanes per node.
+template <bool EXACT>
+__device__ __forceinline__ void pull_forward(const GraphView& g, int q, bool save_h1, float* h1g, bool want_sums,
+                                             float4& msum, float4& hsum) {
+  for (int task = threadIdx.x; task < g.n * 4; task += NT) {
+    const int i = g.ord[task >> 2];
+    const F2x2 epi = ldp(g.EPQ + i * 32 + q * 4), eqi = ldp(g.EPQ + i * 32 + 16 + q * 4);
+    const int beg = g.rp[i], end = g.rp[i + 1];
+    float2 s0 = make_float2(0.f, 0.f), s1 = s0, s2 = s0, s3 = s0;
+    int t = beg;
+    for (; t + 1 < end; t += 2) {       // two neighbours per trip: four independent dependency chains
+      const int k0 = g.adj[t] & 0xffffu, k1 = g.adj[t + 1] & 0xffffu;
+      const F2x2 ep0 = ldp(g.EPQ + k0 * 32 + q * 4), eq0 = ldp(g.EPQ + k0 * 32 + 16 + q * 4);
+      const F2x2 ep1 = ldp(g.EPQ + k1 * 32 + q * 4), eq1 = ldp(g.EPQ + k1 * 32 + 16 + q * 4);
+      fwd_term<EXACT>(epi.a, eqi.a, ep0.a, eq0.a, s0);
+      fwd_term<EXACT>(epi.b, eqi.b, ep0.b, eq0.b, s1);
+      fwd_term<EXACT>(epi.a, eqi.a, ep1.a, eq1.a, s2);
+      fwd_term<EXACT>(epi.b, eqi.b, ep1.b, eq1.b, s3);
+    }
+    if (t < end) {
+      const int k0 = g.adj[t] & 0xffffu;
+      const F2x2 ep0 = ldp(g.EPQ + k0 * 32 + q * 4), eq0 = ldp(g.EPQ + k0 * 32 + 16 + q * 4);
+      fwd_term<EXACT>(epi.a, eqi.a, ep0.a, eq0.a, s0);
+      fwd_term<EXACT>(epi.b, eqi.b, ep0.b, eq0.b, s1);
+    }
+    const float cnt = (float)(end - beg);
+    const float4 acc = make_float4(cnt - (s0.x + s2.x), cnt - (s0.y + s2.y), cnt - (s1.x + s3.x), cnt - (s1.y + s3.y));
+    const float iv = g.inv[i];
+    float4 h = ld4(g.H + i * 16 + q * 4);
+    h.x = fmaf(acc.x, iv, h.x); h.y = fmaf(acc.y, iv, h.y); h.z = fmaf(acc.z, iv, h.z); h.w = fmaf(acc.w, iv, h.w);
+    st4(g.H + i * 16 + q * 4, h);
+    if (save_h1) st4(h1g + i * 16 + q * 4, h);
+    if (want_sums) { msum = msum + acc; hsum = hsum + h; }
+  }
+}
+
+// one GCN layer backward (pull): GPQ[i] = (gP_i | gQ_i) from g_h' (in H), EPQ and, on the last layer, the mean /
+// head gradients of the edge activations.  Returns this thread's share of sum_i gP_i (bias gradient).
+template <bool EXACT>
+__device__ __forceinline__ float4 pull_backward(const GraphView& g, int q, float4 ce4, bool use_head) {
+  float4 bsum = f4(0.f);
+  const float2 two = make_float2(2.f, 2.f);
+  for (int task = threadIdx.x; task < g.n * 4; task += NT) {
+    const int i = g.ord[task >> 2];
+    const F2x2 epi = ldp(g.EPQ + i * 32 + q * 4), eqi = ldp(g.EPQ + i * 32 + 16 + q * 4);
+    const float4 gsi4 = (ld4(g.H + i * 16 + q * 4) * g.inv[i] + ce4) * 2.f;     // 2 (g_h'_i/(deg_i+eps) + g_me/e)
+    const float2 gsa = make_float2(gsi4.x, gsi4.y), gsb = make_float2(gsi4.z, gsi4.w);
+    const int beg = g.rp[i], end = g.rp[i + 1];
+    float2 pa = make_float2(0.f, 0.f), pb = pa, qa = pa, qb = pa;
+    for (int t = beg; t < end; ++t) {
+      const uint32_t ent = g.adj[t];
+      const int k = ent & 0xffffu;
+      const F2x2 epk = ldp(g.EPQ + k * 32 + q * 4), eqk = ldp(g.EPQ + k * 32 + 16 + q * 4);
+      const F2x2 hk = ldp(g.H + k * 16 + q * 4);
+      const float iv2 = 2.f * g.inv[k];
+      const float2 iv22 = make_float2(iv2, iv2);
+      float2 gea = __ffma2_rn(hk.a, iv22, gsa), geb = __ffma2_rn(hk.b, iv22, gsb);
+      if (use_head && (ent >> 16)) {
+        const F2x2 gh = ldp(g.ghead + (size_t)((ent >> 16) - 1) * 16 + q * 4);
+        gea = __ffma2_rn(gh.a, two, gea);
+        geb = __ffma2_rn(gh.b, two, geb);
+      }
+      bwd_term<EXACT>(epi.a, eqi.a, epk.a, eqk.a, gea, pa, qa);
+      bwd_term<EXACT>(epi.b, eqi.b, epk.b, eqk.b, geb, pb, qb);
+    }
+    const float4 aP = make_float4(pa.x, pa.y, pb.x, pb.y);
+    st4(g.GPQ + i * 32 + q * 4, aP);
+    st4(g.GPQ + i * 32 + 16 + q * 4, make_float4(qa.x, qa.y, qb.x, qb.y));
+    bsum = bsum + aP;
+  }
+  return bsum;
 }
 
 // hidden activations of the policy head for one candidate (warp-wide; lane = hidden unit).
@@ -394,6 +508,7 @@ __device__ void graph_body(const StepArgs& a, const BlobHeader& hd, const GraphD
   const float* gnum = reinterpret_cast<const float*>(a.blob + hd.off_num) + (size_t)gid * NUMD;
   const float* gcur = reinterpret_cast<const float*>(a.blob + hd.off_cur) + (size_t)gid * FS;
   const uint16_t* rp_g = reinterpret_cast<const uint16_t*>(a.blob + hd.off_rowptr) + d.rp_off;
+  const uint16_t* ord_g = reinterpret_cast<const uint16_t*>(a.blob + hd.off_order) + d.rp_off;
   const uint32_t* adj_g = reinterpret_cast<const uint32_t*>(a.blob + hd.off_adj) + d.adj_off;
   const uint32_t* cuv_g = reinterpret_cast<const uint32_t*>(a.blob + hd.off_cand_uv) + d.cand_off;
   const int* cidx_g = reinterpret_cast<const int*>(a.blob + hd.off_cand_idx) + d.cand_off;
@@ -411,7 +526,7 @@ __device__ void graph_body(const StepArgs& a, const BlobHeader& hd, const GraphD
     g.z = b;    b += kcap;
     g.gz = b;   b += kcap;
     g.ghead = b;
-    g.rp = rp_g; g.adj = adj_g; g.cuv = cuv_g; g.cidx = cidx_g;
+    g.rp = rp_g; g.adj = adj_g; g.cuv = cuv_g; g.cidx = cidx_g; g.ord = ord_g;
   } else {
     g.EPQ = smem + S_EPQ; g.GPQ = smem + S_GPQ; g.H = smem + S_H; g.inv = smem + S_INV;
     g.alpha = smem + S_ALPHA; g.z = smem + S_Z; g.gz = smem + S_GZ; g.ghead = smem + S_GHEAD;
@@ -424,6 +539,9 @@ __device__ void graph_body(const StepArgs& a, const BlobHeader& hd, const GraphD
       const uint4* s0 = reinterpret_cast<const uint4*>(rp_g);
       uint4* d0 = reinterpret_cast<uint4*>(rp_s);
       for (int i = tid; i < (n + 1 + 7) / 8; i += NT) d0[i] = s0[i];
+      const uint4* so = reinterpret_cast<const uint4*>(ord_g);
+      uint4* dord = reinterpret_cast<uint4*>(smem + S_ORD);
+      for (int i = tid; i < (n + 7) / 8; i += NT) dord[i] = so[i];
       const uint4* s1 = reinterpret_cast<const uint4*>(adj_g);
       uint4* d1 = reinterpret_cast<uint4*>(adj_s);
       for (int i = tid; i < (2 * e + 3) / 4; i += NT) d1[i] = s1[i];
@@ -434,6 +552,7 @@ __device__ void graph_body(const StepArgs& a, const BlobHeader& hd, const GraphD
       for (int i = tid; i < (k + 3) / 4; i += NT) { d2[i] = s2[i]; d3[i] = s3[i]; }
     }
     g.rp = rp_s; g.adj = adj_s; g.cuv = cuv_s; g.cidx = cidx_s;
+    g.ord = reinterpret_cast<const uint16_t*>(smem + S_ORD);
   }
   if (tid < NUMD) sV[V_X52 + tid] = gnum[tid];
   if (tid >= 64 && tid < 64 + FS) sV[V_XCUR + tid - 64] = gcur[tid - 64];
@@ -472,44 +591,14 @@ __device__ void graph_body(const StepArgs& a, const BlobHeader& hd, const GraphD
   matvec8<true>(P + P_NUM_W1, P + P_NUM_B1, 16, NH0, sV + V_A0, sV + V_SV);
 
   // GCN layers (state_encoder.py:194-197): h <- h + (sum_{nbr} he) / (deg + eps), pull over the CSR
+  int exact_last = 0;
   for (int l = 0; l < 2; ++l) {
-    epq_phase(g, g.H, sW + (l == 0 ? S_WPQT0 : S_WPQT1), sW + (l == 0 ? S_B0 : S_B1));
-    __syncthreads();
+    const int bad = epq_phase(g, g.H, sW + (l == 0 ? S_WPQT0 : S_WPQT1), sW + (l == 0 ? S_B0 : S_B1));
+    const int exact = __syncthreads_or(bad);     // any pre-activation outside the one-reciprocal range?
+    if (l == 1) exact_last = exact;
     float4 msum = f4(0.f), hsum = f4(0.f);
-    for (int task = tid; task < n * 4; task += NT) {
-      const int i = task >> 2;
-      const float4 epi = ld4(g.EPQ + i * 32 + q * 4), eqi = ld4(g.EPQ + i * 32 + 16 + q * 4);
-      const int beg = g.rp[i], end = g.rp[i + 1];
-      float4 acc = f4(0.f);
-      for (int t = beg; t < end; t += 2) {       // two neighbours per trip for memory-level parallelism
-        const bool two = t + 1 < end;
-        const int k0 = g.adj[t] & 0xffffu;
-        const int k1 = two ? (int)(g.adj[t + 1] & 0xffffu) : k0;
-        const float4 ep0 = ld4(g.EPQ + k0 * 32 + q * 4), eq0 = ld4(g.EPQ + k0 * 32 + 16 + q * 4);
-        const float4 ep1 = ld4(g.EPQ + k1 * 32 + q * 4), eq1 = ld4(g.EPQ + k1 * 32 + 16 + q * 4);
-        float4 c0, c1;
-        c0.x = (1.f - rcp_approx(fmaf(epi.x, eq0.x, 1.f))) - rcp_approx(fmaf(ep0.x, eqi.x, 1.f));
-        c0.y = (1.f - rcp_approx(fmaf(epi.y, eq0.y, 1.f))) - rcp_approx(fmaf(ep0.y, eqi.y, 1.f));
-        c0.z = (1.f - rcp_approx(fmaf(epi.z, eq0.z, 1.f))) - rcp_approx(fmaf(ep0.z, eqi.z, 1.f));
-        c0.w = (1.f - rcp_approx(fmaf(epi.w, eq0.w, 1.f))) - rcp_approx(fmaf(ep0.w, eqi.w, 1.f));
-        c1.x = (1.f - rcp_approx(fmaf(epi.x, eq1.x, 1.f))) - rcp_approx(fmaf(ep1.x, eqi.x, 1.f));
-        c1.y = (1.f - rcp_approx(fmaf(epi.y, eq1.y, 1.f))) - rcp_approx(fmaf(ep1.y, eqi.y, 1.f));
-        c1.z = (1.f - rcp_approx(fmaf(epi.z, eq1.z, 1.f))) - rcp_approx(fmaf(ep1.z, eqi.z, 1.f));
-        c1.w = (1.f - rcp_approx(fmaf(epi.w, eq1.w, 1.f))) - rcp_approx(fmaf(ep1.w, eqi.w, 1.f));
-        acc = acc + c0;
-        if (two) acc = acc + c1;
-      }
-      const float iv = g.inv[i];
-      float4 h = ld4(g.H + i * 16 + q * 4);
-      h.x = fmaf(acc.x, iv, h.x); h.y = fmaf(acc.y, iv, h.y); h.z = fmaf(acc.z, iv, h.z); h.w = fmaf(acc.w, iv, h.w);
-      st4(g.H + i * 16 + q * 4, h);
-      if (l == 0) {
-        if (TRAIN) st4(g.H1g + i * 16 + q * 4, h);
-      } else {
-        msum = msum + acc;
-        hsum = hsum + h;
-      }
-    }
+    if (exact) pull_forward<true>(g, q, TRAIN && l == 0, g.H1g, l == 1, msum, hsum);
+    else pull_forward<false>(g, q, TRAIN && l == 0, g.H1g, l == 1, msum, hsum);
     if (l == 1) {   // masked means (state_encoder.py:179-182,199-200); sum_j he_j = 1/2 sum_i acc_i
       block_sum_q4(msum, sRed, sV + V_TMP16);
       block_sum_q4(hsum, sRed, sV + V_TMP16B);
@@ -887,51 +976,15 @@ __device__ void graph_body(const StepArgs& a, const BlobHeader& hd, const GraphD
   for (int l = 1; l >= 0; --l) {
     const float* Wpq = sW + (l == 0 ? S_WPQ0 : S_WPQ1);
     const float* hin = l == 0 ? g.H0g : g.H1g;     // layer input h^l (global scratch)
+    int exact = exact_last;
     if (l == 0) {   // EPQ of layer 0 was overwritten by layer 1: recompute from h^0
-      epq_phase(g, hin, sW + S_WPQT0, sW + S_B0);
-      __syncthreads();
+      const int bad = epq_phase(g, hin, sW + S_WPQT0, sW + S_B0);
+      exact = __syncthreads_or(bad);
     }
     const bool last = (l == 1);
     const float4 ce4 = last ? ld4(sV + V_CE + q * 4) : f4(0.f);
     const bool use_head = last && g.stage == 0;
-    float4 bsum = f4(0.f);
-    for (int task = tid; task < n * 4; task += NT) {
-      const int i = task >> 2;
-      const float4 epi = ld4(g.EPQ + i * 32 + q * 4), eqi = ld4(g.EPQ + i * 32 + 16 + q * 4);
-      const float4 gsi = ld4(g.H + i * 16 + q * 4) * g.inv[i] + ce4;
-      const int beg = g.rp[i], end = g.rp[i + 1];
-      float4 aP = f4(0.f), aQ = f4(0.f);
-      for (int t = beg; t < end; t += 2) {
-        const bool two = t + 1 < end;
-        const uint32_t ent0 = g.adj[t];
-        const uint32_t ent1 = two ? g.adj[t + 1] : ent0;
-        const int k0 = ent0 & 0xffffu, k1 = ent1 & 0xffffu;
-        const float4 ep0 = ld4(g.EPQ + k0 * 32 + q * 4), eq0 = ld4(g.EPQ + k0 * 32 + 16 + q * 4);
-        const float4 ep1 = ld4(g.EPQ + k1 * 32 + q * 4), eq1 = ld4(g.EPQ + k1 * 32 + 16 + q * 4);
-        float4 ge0 = gsi + ld4(g.H + k0 * 16 + q * 4) * g.inv[k0];
-        float4 ge1 = gsi + ld4(g.H + k1 * 16 + q * 4) * g.inv[k1];
-        if (use_head) {
-          if (ent0 >> 16) ge0 = ge0 + ld4(g.ghead + (size_t)((ent0 >> 16) - 1) * 16 + q * 4);
-          if (ent1 >> 16) ge1 = ge1 + ld4(g.ghead + (size_t)((ent1 >> 16) - 1) * 16 + q * 4);
-        }
-        if (!two) ge1 = f4(0.f);
-        float r;
-        // d tanh = 1 - t^2 = 4 r (1 - r);  g1 = ge/2 * (1 - t1^2) = 2 ge r1 (1 - r1)
-#define UPB_BWD_TERM(EA, EB, GE, ACC) r = rcp_approx(fmaf(EA, EB, 1.f)); ACC = fmaf(GE, 2.f * r * (1.f - r), ACC);
-        UPB_BWD_TERM(epi.x, eq0.x, ge0.x, aP.x) UPB_BWD_TERM(epi.y, eq0.y, ge0.y, aP.y)
-        UPB_BWD_TERM(epi.z, eq0.z, ge0.z, aP.z) UPB_BWD_TERM(epi.w, eq0.w, ge0.w, aP.w)
-        UPB_BWD_TERM(ep0.x, eqi.x, ge0.x, aQ.x) UPB_BWD_TERM(ep0.y, eqi.y, ge0.y, aQ.y)
-        UPB_BWD_TERM(ep0.z, eqi.z, ge0.z, aQ.z) UPB_BWD_TERM(ep0.w, eqi.w, ge0.w, aQ.w)
-        UPB_BWD_TERM(epi.x, eq1.x, ge1.x, aP.x) UPB_BWD_TERM(epi.y, eq1.y, ge1.y, aP.y)
-        UPB_BWD_TERM(epi.z, eq1.z, ge1.z, aP.z) UPB_BWD_TERM(epi.w, eq1.w, ge1.w, aP.w)
-        UPB_BWD_TERM(ep1.x, eqi.x, ge1.x, aQ.x) UPB_BWD_TERM(ep1.y, eqi.y, ge1.y, aQ.y)
-        UPB_BWD_TERM(ep1.z, eqi.z, ge1.z, aQ.z) UPB_BWD_TERM(ep1.w, eqi.w, ge1.w, aQ.w)
-#undef UPB_BWD_TERM
-      }
-      st4(g.GPQ + i * 32 + q * 4, aP);
-      st4(g.GPQ + i * 32 + 16 + q * 4, aQ);
-      bsum = bsum + aP;
-    }
+    const float4 bsum = exact ? pull_backward<true>(g, q, ce4, use_head) : pull_backward<false>(g, q, ce4, use_head);
     block_sum_q4(bsum, sRed, sV + V_TMP16);     // barriers inside: GPQ complete, EPQ dead
     if (tid < 16) gacc(gp, (l == 0 ? P_GCN0_B : P_GCN1_B) + tid, sV[V_TMP16 + tid]);
     {   // g_W[o][c] = sum_i GPQ[i][o] h^l[i][c]: 4x4 register tiles, K split over the 16 warps

@@ -29,6 +29,8 @@ def check_blob(states, blob):
         adj = d["adj"][g["adj_off"]:g["adj_off"] + 2 * e]
         deg = np.bincount(ei[:e, 0], minlength=n) + np.bincount(ei[:e, 1], minlength=n)
         assert rp[0] == 0 and np.array_equal(np.diff(rp), deg)
+        order = d["order"][g["rp_off"]:g["rp_off"] + n].astype(np.int64)
+        assert sorted(order.tolist()) == list(range(n)) and (np.diff(deg[order]) <= 0).all()
         # the symmetrised adjacency holds every undirected edge exactly twice (once per endpoint)
         got = sorted((min(i_, int(a & 0xffff)), max(i_, int(a & 0xffff)))
                      for i_ in range(n) for a in adj[rp[i_]:rp[i_ + 1]])
