@@ -30,8 +30,8 @@ namespace upb {
 constexpr int NT = 512;          // threads per CTA
 constexpr int NW = NT / 32;      // warps per CTA
 constexpr int NS = 464;          // nodes kept in shared memory
-constexpr int AS = 5120;         // directed adjacency entries kept in shared memory
-constexpr int KS = 256;          // action candidates kept in shared memory
+constexpr int AS = 5632;         // directed adjacency entries kept in shared memory
+constexpr int KS = 160;          // action candidates kept in shared memory
 constexpr int CH = 64;           // candidate chunk of the head backward
 constexpr float MASK_FILL = -4294967296.0f;   // float32(-2**32 + 1), policy.py:50
 constexpr float EPS_DEG = 1e-6f;               // state_encoder.py:11
@@ -94,7 +94,8 @@ constexpr int V_GW2 = 1768;     // [32]
 constexpr int V_TMP16 = 1800;   // [16] block-reduce results
 constexpr int V_TMP16B = 1816;  // [16]
 constexpr int V_SC = 1832;      // [24] scalars
-constexpr int V_END = 1856;
+constexpr int V_WEFF = 1856;    // [32][16] Weff (land use), row-major copy for the head backward
+constexpr int V_END = 2368;
 // scalar slots
 constexpr int SC_VALUE = 0, SC_MAX = 1, SC_SUM = 2, SC_LSE = 3, SC_ENT = 4, SC_LOGP = 5, SC_GV = 6, SC_GLP = 7,
               SC_GH = 8, SC_Z = 9, SC_SLOT = 10, SC_BEST = 11, SC_GDOT = 12;
@@ -271,6 +272,7 @@ __device__ __forceinline__ void matvec8(const float* __restrict__ W, const float
   for (int row = threadIdx.x >> 3; row < rows; row += NT / 8) {
     const float* w = W + (size_t)row * cols;
     float acc = 0.f;
+#pragma unroll 9
     for (int k = p; k < cols; k += 8) acc = fmaf(__ldg(w + k), x[k], acc);
     acc += __shfl_xor_sync(0xffffffffu, acc, 1);
     acc += __shfl_xor_sync(0xffffffffu, acc, 2);
@@ -489,7 +491,12 @@ __device__ __forceinline__ void head_unit(const GraphView& g, int j, const float
 }
 
 // own-thread read-modify-write on this CTA's private gradient row (same thread always owns the same element)
-__device__ __forceinline__ void gacc(float* gp, int idx, float v) { gp[idx] += v; }
+// contribution of this graph to the CTA-private gradient row.  `red.global.add` has no return value, so the
+// thread does not wait for the L2 round trip; the row is private to the CTA and every element is always updated
+// by the same thread, so the summation order stays fixed (deterministic).
+__device__ __forceinline__ void gacc(float* gp, int idx, float v) {
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(gp + idx), "f"(v) : "memory");
+}
 
 template <bool TRAIN, bool BIG>
 __device__ void graph_body(const StepArgs& a, const BlobHeader& hd, const GraphDesc& d, int gid, float* smem,
@@ -684,7 +691,9 @@ __device__ void graph_body(const StepArgs& a, const BlobHeader& hd, const GraphD
     {   // Weff = Wa + Wd + Wc diag(hc), ceff = b + (Wb - Wd) hc   (state_encoder.py:207-210 folded into the head)
       const int r = tid >> 4, c = tid & 15;
       const float* w = sW + S_LUW0 + r * 64;
-      sV[V_WEFFT + c * 32 + r] = w[c] + w[48 + c] + w[32 + c] * sV[V_HC + c];
+      const float weff = w[c] + w[48 + c] + w[32 + c] * sV[V_HC + c];
+      sV[V_WEFFT + c * 32 + r] = weff;
+      sV[V_WEFF + r * 16 + c] = weff;
       if (tid < 32) {
         const float* wr = sW + S_LUW0 + tid * 64;
         float s = sW[S_LUB0 + tid];
@@ -811,7 +820,7 @@ __device__ void graph_body(const StepArgs& a, const BlobHeader& hd, const GraphD
     float* cX = cGT + CH * 32;              // [CH][16] head input
     float G = 0.f, gcr = 0.f, gw2r = 0.f;   // thread (r = tid>>4, c = tid&15)
     const int r_ = tid >> 4, c_ = tid & 15;
-    const float* WT = g.stage == 0 ? sV + V_WEFFT : sW + S_RDW0T;   // [16][32]
+    const float* WR = g.stage == 0 ? sV + V_WEFF : sW + S_RDW0;     // [32][16] row-major (conflict-free below)
     for (int base = 0; base < k; base += CH) {
       const int cn = min(CH, k - base);
       for (int jj = warp; jj < cn; jj += NW) {
@@ -832,7 +841,7 @@ __device__ void graph_body(const StepArgs& a, const BlobHeader& hd, const GraphD
         const int jj = task >> 4, c = task & 15;
         float s = 0.f;
 #pragma unroll 8
-        for (int r = 0; r < 32; ++r) s = fmaf(WT[c * 32 + r], cGU[jj * 32 + r], s);
+        for (int r = 0; r < 32; ++r) s = fmaf(WR[r * 16 + c], cGU[jj * 32 + r], s);
         g.ghead[(size_t)(base + jj) * 16 + c] = s;
       }
       __syncthreads();
@@ -868,12 +877,14 @@ __device__ void graph_body(const StepArgs& a, const BlobHeader& hd, const GraphD
   __syncthreads();
   if (tid < 32) {
     float s = 0.f;
+#pragma unroll
     for (int r = 0; r < 32; ++r) s = fmaf(__ldg(P + P_VAL_W1 + r * 32 + tid), sV[V_D1 + r], s);
     sV[V_D0 + tid] = s * (1.f - sV[V_Y0 + tid] * sV[V_Y0 + tid]);
   }
   __syncthreads();
   if (tid < SVD) {
     float s = 0.f;
+#pragma unroll
     for (int r = 0; r < 32; ++r) s = fmaf(__ldg(P + P_VAL_W0 + r * SVD + tid), sV[V_D0 + r], s);
     sV[V_GSV + tid] = s;
   }
@@ -891,6 +902,7 @@ __device__ void graph_body(const StepArgs& a, const BlobHeader& hd, const GraphD
   __syncthreads();
   if (tid < NH0) {
     float s = 0.f;
+#pragma unroll
     for (int r = 0; r < 16; ++r) s = fmaf(__ldg(P + P_NUM_W1 + r * NH0 + tid), sV[V_DN1 + r], s);
     sV[V_DN0 + tid] = s * (1.f - sV[V_A0 + tid] * sV[V_A0 + tid]);
   }

@@ -128,7 +128,7 @@ def test_matches_numpy_oracle(community, count, seed, dev):
 
 
 def big_states(seed, count):
-    """Graphs beyond the shared-memory fast path (n > 464 or 2e > 5120 or > 256 candidates), up to the caps."""
+    """Graphs beyond the shared-memory fast path (n > 464 or 2e > 5632 or > 160 candidates), up to the caps."""
     spec = synth.CommunitySpec("big", 1000, 3000, 470, 1000, 3.0, 0.3)
     rng = np.random.default_rng(seed)
     states, actions = [], np.zeros((count, 2), np.float32)
@@ -154,7 +154,7 @@ def test_large_graph_path_matches_numpy_oracle(dev):
     ref = ON.ppo_minibatch(flat, states, actions, adv, ret, fixed, exps)
     blob = pack_states(states).to(dev)
     info = blob.info
-    assert (info[:, 0] > 464).any() and (info[:, 2] > 256).any()
+    assert (info[:, 0] > 464).any() and (info[:, 2] > 160).any()
     eng = make_engine(dev, blob.n_cap, blob.e_cap)
     params = t(flat, dev)
     value, logp, ent = eng.forward(blob, params, t(actions, dev))
