@@ -27,7 +27,9 @@ struct upb_ctx {
   size_t scratch_stride = 0;
   float* adam_m = nullptr;
   float* adam_v = nullptr;
-  long long* steps = nullptr;   // device [4]
+  long long* steps = nullptr;   // device [2][4] ping-pong step counters
+  int steps_cur = 0;
+  unsigned int* ticket = nullptr;
   float* host_pinned = nullptr; // [UPB_STAT_COUNT] pinned staging for upb_read_losses
   int64_t launches = 0;
   bool profiling = false;
@@ -154,10 +156,12 @@ extern "C" int upb_create(const upb_config* cfg, upb_ctx** out) {
   UPB_CUDA_F(cudaMalloc(&ctx->scratch, sizeof(float) * (size_t)ctx->grid * ctx->scratch_stride));
   UPB_CUDA_F(cudaMalloc(&ctx->adam_m, sizeof(float) * NUM_PARAMS));
   UPB_CUDA_F(cudaMalloc(&ctx->adam_v, sizeof(float) * NUM_PARAMS));
-  UPB_CUDA_F(cudaMalloc(&ctx->steps, sizeof(long long) * 4));
+  UPB_CUDA_F(cudaMalloc(&ctx->steps, sizeof(long long) * 8));
+  UPB_CUDA_F(cudaMalloc(&ctx->ticket, sizeof(unsigned int)));
+  UPB_CUDA_F(cudaMemset(ctx->ticket, 0, sizeof(unsigned int)));
   UPB_CUDA_F(cudaMemset(ctx->adam_m, 0, sizeof(float) * NUM_PARAMS));
   UPB_CUDA_F(cudaMemset(ctx->adam_v, 0, sizeof(float) * NUM_PARAMS));
-  UPB_CUDA_F(cudaMemset(ctx->steps, 0, sizeof(long long) * 4));
+  UPB_CUDA_F(cudaMemset(ctx->steps, 0, sizeof(long long) * 8));
   UPB_CUDA_F(cudaMemset(ctx->scratch, 0, sizeof(float) * (size_t)ctx->grid * ctx->scratch_stride));
   UPB_CUDA_F(cudaMallocHost(&ctx->host_pinned, sizeof(float) * UPB_STAT_COUNT));
   UPB_CUDA_F(cudaFuncSetAttribute(k_sgnn<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
@@ -176,6 +180,7 @@ extern "C" void upb_destroy(upb_ctx* ctx) {
   cudaFree(ctx->adam_m);
   cudaFree(ctx->adam_v);
   cudaFree(ctx->steps);
+  cudaFree(ctx->ticket);
   if (ctx->host_pinned) cudaFreeHost(ctx->host_pinned);
   for (auto& ev : ctx->prof_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
   delete ctx;
@@ -224,9 +229,8 @@ extern "C" int upb_ppo_grad(upb_ctx* ctx, const void* blob_dev, const int32_t* i
     prof_end(ctx, s, prof);
     ctx->launches += 1;
   }
-  k_reduce_partials<<<(G_ROW + 255) / 256, 256, 0, s>>>(ctx->gpart, grid, ctx->gsum);
-  k_finish_grad<<<1, 256, 0, s>>>(ctx->gsum, params, grad_out);
-  ctx->launches += 2;
+  k_reduce_finish<<<RF_BLOCKS, RF_THREADS, 0, s>>>(ctx->gpart, grid, ctx->gsum, params, grad_out, ctx->ticket);
+  ctx->launches += 1;
   UPB_CUDA(cudaGetLastError());
   return UPB_OK;
 }
@@ -239,13 +243,15 @@ extern "C" int upb_apply(upb_ctx* ctx, float* params, const float* grad, void* s
   a.grad = grad;
   a.m = ctx->adam_m;
   a.v = ctx->adam_v;
-  a.steps = ctx->steps;
+  a.steps_in = ctx->steps + 4 * ctx->steps_cur;
+  a.steps_out = ctx->steps + 4 * (1 - ctx->steps_cur);
+  ctx->steps_cur = 1 - ctx->steps_cur;
   a.lr = ctx->cfg.lr;
   a.beta1 = ctx->cfg.beta1;
   a.beta2 = ctx->cfg.beta2;
   a.eps = ctx->cfg.adam_eps;
   a.clip_mode = ctx->cfg.clip_mode;
-  k_apply<<<1, 1024, 0, (cudaStream_t)stream>>>(a);
+  k_apply<<<AP_BLOCKS, AP_THREADS, 0, (cudaStream_t)stream>>>(a);
   ctx->launches += 1;
   UPB_CUDA(cudaGetLastError());
   return UPB_OK;
@@ -285,7 +291,8 @@ extern "C" int upb_get_opt_state(upb_ctx* ctx, float* m_host, float* v_host, int
   UPB_CUDA(cudaDeviceSynchronize());
   if (m_host) UPB_CUDA(cudaMemcpy(m_host, ctx->adam_m, sizeof(float) * NUM_PARAMS, cudaMemcpyDeviceToHost));
   if (v_host) UPB_CUDA(cudaMemcpy(v_host, ctx->adam_v, sizeof(float) * NUM_PARAMS, cudaMemcpyDeviceToHost));
-  if (steps4_host) UPB_CUDA(cudaMemcpy(steps4_host, ctx->steps, sizeof(long long) * 4, cudaMemcpyDeviceToHost));
+  if (steps4_host)
+    UPB_CUDA(cudaMemcpy(steps4_host, ctx->steps + 4 * ctx->steps_cur, sizeof(long long) * 4, cudaMemcpyDeviceToHost));
   return UPB_OK;
 }
 
@@ -295,7 +302,8 @@ extern "C" int upb_set_opt_state(upb_ctx* ctx, const float* m_host, const float*
   UPB_CUDA(cudaDeviceSynchronize());
   if (m_host) UPB_CUDA(cudaMemcpy(ctx->adam_m, m_host, sizeof(float) * NUM_PARAMS, cudaMemcpyHostToDevice));
   if (v_host) UPB_CUDA(cudaMemcpy(ctx->adam_v, v_host, sizeof(float) * NUM_PARAMS, cudaMemcpyHostToDevice));
-  if (steps4_host) UPB_CUDA(cudaMemcpy(ctx->steps, steps4_host, sizeof(long long) * 4, cudaMemcpyHostToDevice));
+  if (steps4_host)
+    UPB_CUDA(cudaMemcpy(ctx->steps + 4 * ctx->steps_cur, steps4_host, sizeof(long long) * 4, cudaMemcpyHostToDevice));
   return UPB_OK;
 }
 
