@@ -27,7 +27,7 @@
 
 namespace upb {
 
-constexpr int NT = 512;          // threads per CTA
+constexpr int NT = 512;          // threads per CTA (1024 measured slower: spills + costlier barriers, profiles/)
 constexpr int NW = NT / 32;      // warps per CTA
 constexpr int NS = 464;          // nodes kept in shared memory
 constexpr int AS = 5632;         // directed adjacency entries kept in shared memory
@@ -118,7 +118,9 @@ constexpr int S_H = S_GPQ + NS * 32;             // [NS][16]
 constexpr int S_TOTAL = S_H + NS * 16;
 constexpr size_t SMEM_BYTES = (size_t)S_TOTAL * 4;
 static_assert(SMEM_BYTES <= 232448, "shared memory budget (227 KB)");
-static_assert(NW * 512 <= NS * 32, "cross-warp reduction buffer aliases the EPQ region");
+constexpr int KW = 16;            // warps that share the K dimension of the g_W tile reduction
+static_assert(KW * 512 <= NS * 32 && NW * 384 <= NS * 32, "cross-warp reduction buffers alias the EPQ region");
+static_assert(NT >= 512 && KW <= NW, "thread (r, c) = (tid >> 4, tid & 15) mappings use the first 512 threads");
 static_assert(CH * (32 + 32 + 16) <= NS * 32, "chunk buffers alias the GPQ region");
 
 // per-CTA global scratch (floats): saved layer inputs + big-graph arrays
@@ -147,6 +149,7 @@ struct StepArgs {
   float* scratch;      // [gridDim.x][scratch_stride]
   size_t scratch_stride;
   int n_cap, e_cap;
+  long long* stamps;   // optional [64] clock64() phase stamps of the first graph of CTA 0 (tools/phase_times.py)
 };
 
 // ---- small device helpers ------------------------------------------------------------------------------
@@ -498,11 +501,17 @@ __device__ __forceinline__ void gacc(float* gp, int idx, float v) {
   asm volatile("red.global.add.f32 [%0], %1;" ::"l"(gp + idx), "f"(v) : "memory");
 }
 
+#define UPB_STAMP(ID)                                                                      \
+  do {                                                                                     \
+    if (a.stamps != nullptr && blockIdx.x == 0 && threadIdx.x == 0 && first_item) a.stamps[ID] = clock64(); \
+  } while (0)
+
 template <bool TRAIN, bool BIG>
 __device__ void graph_body(const StepArgs& a, const BlobHeader& hd, const GraphDesc& d, int gid, float* smem,
-                           float* gp, float* scr) {
+                           float* gp, float* scr, bool first_item) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int q = tid & 3;
+  UPB_STAMP(0);
   float* sW = smem;
   float* sV = smem + S_VEC;
   float* sRed = smem + S_RED;
@@ -565,6 +574,7 @@ __device__ void graph_body(const StepArgs& a, const BlobHeader& hd, const GraphD
   if (tid >= 64 && tid < 64 + FS) sV[V_XCUR + tid - 64] = gcur[tid - 64];
   if (tid < 24) sc[tid] = 0.f;
   __syncthreads();
+  UPB_STAMP(1);
 
   // ================================================================================ forward
   for (int i = tid; i < n; i += NT) g.inv[i] = 1.0f / ((float)(g.rp[i + 1] - g.rp[i]) + EPS_DEG);
@@ -595,6 +605,7 @@ __device__ void graph_body(const StepArgs& a, const BlobHeader& hd, const GraphD
   // numeric feature encoder, first layer (state_encoder.py:35-57,187)
   matvec8<true>(P + P_NUM_W0, P + P_NUM_B0, NH0, NUMD, sV + V_X52, sV + V_A0);
   __syncthreads();
+  UPB_STAMP(2);
   matvec8<true>(P + P_NUM_W1, P + P_NUM_B1, 16, NH0, sV + V_A0, sV + V_SV);
 
   // GCN layers (state_encoder.py:194-197): h <- h + (sum_{nbr} he) / (deg + eps), pull over the CSR
@@ -602,6 +613,7 @@ __device__ void graph_body(const StepArgs& a, const BlobHeader& hd, const GraphD
   for (int l = 0; l < 2; ++l) {
     const int bad = epq_phase(g, g.H, sW + (l == 0 ? S_WPQT0 : S_WPQT1), sW + (l == 0 ? S_B0 : S_B1));
     const int exact = __syncthreads_or(bad);     // any pre-activation outside the one-reciprocal range?
+    UPB_STAMP(3+l*2);
     if (l == 1) exact_last = exact;
     float4 msum = f4(0.f), hsum = f4(0.f);
     if (exact) pull_forward<true>(g, q, TRAIN && l == 0, g.H1g, l == 1, msum, hsum);
@@ -615,6 +627,7 @@ __device__ void graph_body(const StepArgs& a, const BlobHeader& hd, const GraphD
       }
     }
     __syncthreads();
+    UPB_STAMP(4+l*2);
   }
 
   // attention of the current node over all nodes (state_encoder.py:150-161)
@@ -673,12 +686,14 @@ __device__ void graph_body(const StepArgs& a, const BlobHeader& hd, const GraphD
   }
   if (tid < 3) sV[V_SV + 64 + tid] = (tid == g.stage) ? 1.f : 0.f;
   __syncthreads();
+  UPB_STAMP(7);
 
   // value head (value.py:15-39)
   matvec8<true>(P + P_VAL_W0, P + P_VAL_B0, HID, SVD, sV + V_SV, sV + V_Y0);
   __syncthreads();
   matvec8<true>(P + P_VAL_W1, P + P_VAL_B1, HID, HID, sV + V_Y0, sV + V_Y1);
   __syncthreads();
+  UPB_STAMP(8);
   if (warp == 0) {
     const float v = warp_sum(__ldg(P + P_VAL_W2 + lane) * sV[V_Y1 + lane]) + __ldg(P + P_VAL_B2);
     if (lane == 0) sc[SC_VALUE] = v;
@@ -688,7 +703,7 @@ __device__ void graph_body(const StepArgs& a, const BlobHeader& hd, const GraphD
   float wrow[16];
   float cb, w2;
   if (g.stage == 0) {
-    {   // Weff = Wa + Wd + Wc diag(hc), ceff = b + (Wb - Wd) hc   (state_encoder.py:207-210 folded into the head)
+    if (tid < 512) {   // Weff = Wa + Wd + Wc diag(hc), ceff = b + (Wb - Wd) hc   (state_encoder.py:207-210 folded in)
       const int r = tid >> 4, c = tid & 15;
       const float* w = sW + S_LUW0 + r * 64;
       const float weff = w[c] + w[48 + c] + w[32 + c] * sV[V_HC + c];
@@ -719,6 +734,7 @@ __device__ void graph_body(const StepArgs& a, const BlobHeader& hd, const GraphD
     if (lane == 0) g.z[j] = zj;
   }
   __syncthreads();
+  UPB_STAMP(9);
   {   // masked softmax statistics: log-softmax over the candidates equals log-softmax over all padded logits
     float lmax = -CUDART_INF_F;
     int lbest = 0x7fffffff;
@@ -775,6 +791,7 @@ __device__ void graph_body(const StepArgs& a, const BlobHeader& hd, const GraphD
       if (a.out_greedy) a.out_greedy[gid] = greedy;
     }
     __syncthreads();
+    UPB_STAMP(10);
   }
   if constexpr (!TRAIN) return;
 
@@ -812,6 +829,7 @@ __device__ void graph_body(const StepArgs& a, const BlobHeader& hd, const GraphD
   }
   if (tid < 16) sV[V_GHC + tid] = 0.f;
   __syncthreads();
+  UPB_STAMP(11);
 
   // ---- policy head backward, CH candidates at a time (chunk buffers alias the GPQ region / shared scratch)
   {
@@ -832,10 +850,12 @@ __device__ void graph_body(const StepArgs& a, const BlobHeader& hd, const GraphD
         if (lane < 16) cX[jj * 16 + lane] = xin;
       }
       __syncthreads();
-      for (int jj = 0; jj < cn; ++jj) {
-        const float gu = cGU[jj * 32 + r_];
-        G = fmaf(gu, cX[jj * 16 + c_], G);
-        if (c_ == 0) { gcr += gu; gw2r += cGT[jj * 32 + r_]; }
+      if (tid < 512) {
+        for (int jj = 0; jj < cn; ++jj) {
+          const float gu = cGU[jj * 32 + r_];
+          G = fmaf(gu, cX[jj * 16 + c_], G);
+          if (c_ == 0) { gcr += gu; gw2r += cGT[jj * 32 + r_]; }
+        }
       }
       for (int task = tid; task < cn * 16; task += NT) {   // g_x = W^T g_u
         const int jj = task >> 4, c = task & 15;
@@ -846,16 +866,21 @@ __device__ void graph_body(const StepArgs& a, const BlobHeader& hd, const GraphD
       }
       __syncthreads();
     }
-    sV[V_GWEFF + tid] = G;
-    if (c_ == 0) { sV[V_GC + r_] = gcr; sV[V_GW2 + r_] = gw2r; }
+    if (tid < 512) {
+      sV[V_GWEFF + tid] = G;
+      if (c_ == 0) { sV[V_GC + r_] = gcr; sV[V_GW2 + r_] = gw2r; }
+    }
     __syncthreads();
+    UPB_STAMP(12);
     if (g.stage == 0) {
-      const float hc = sV[V_HC + c_], gc = sV[V_GC + r_];
-      const int o = P_LU_W0 + r_ * 64 + c_;
-      gacc(gp, o, G);
-      gacc(gp, o + 16, gc * hc);
-      gacc(gp, o + 32, G * hc);
-      gacc(gp, o + 48, G - gc * hc);
+      if (tid < 512) {
+        const float hc = sV[V_HC + c_], gc = sV[V_GC + r_];
+        const int o = P_LU_W0 + r_ * 64 + c_;
+        gacc(gp, o, G);
+        gacc(gp, o + 16, gc * hc);
+        gacc(gp, o + 32, G * hc);
+        gacc(gp, o + 48, G - gc * hc);
+      }
       if (tid < 32) { gacc(gp, P_LU_B0 + tid, sV[V_GC + tid]); gacc(gp, P_LU_W1 + tid, sV[V_GW2 + tid]); }
       if (tid < 16) {   // d/d hc through ceff and through Wc diag(hc)
         float s = 0.f;
@@ -867,7 +892,7 @@ __device__ void graph_body(const StepArgs& a, const BlobHeader& hd, const GraphD
         sV[V_GHC + tid] = s;
       }
     } else {
-      gacc(gp, P_RD_W0 + tid, G);
+      if (tid < 512) gacc(gp, P_RD_W0 + tid, G);
       if (tid < 32) { gacc(gp, P_RD_B0 + tid, sV[V_GC + tid]); gacc(gp, P_RD_W1 + tid, sV[V_GW2 + tid]); }
     }
   }
@@ -907,6 +932,7 @@ __device__ void graph_body(const StepArgs& a, const BlobHeader& hd, const GraphD
     sV[V_DN0 + tid] = s * (1.f - sV[V_A0 + tid] * sV[V_A0 + tid]);
   }
   __syncthreads();
+  UPB_STAMP(13);
   for (int idx = tid; idx < 16 * NH0; idx += NT) gacc(gp, P_NUM_W1 + idx, sV[V_DN1 + (idx >> 6)] * sV[V_A0 + (idx & 63)]);
   for (int idx = tid; idx < NH0 * NUMD; idx += NT) gacc(gp, P_NUM_W0 + idx, sV[V_DN0 + idx / NUMD] * sV[V_X52 + idx % NUMD]);
   if (tid < 16) gacc(gp, P_NUM_B1 + tid, sV[V_DN1 + tid]);
@@ -983,6 +1009,7 @@ __device__ void graph_body(const StepArgs& a, const BlobHeader& hd, const GraphD
     }
   }
   __syncthreads();
+  UPB_STAMP(14);
 
   // ---- GCN layers, last to first
   for (int l = 1; l >= 0; --l) {
@@ -992,22 +1019,24 @@ __device__ void graph_body(const StepArgs& a, const BlobHeader& hd, const GraphD
     if (l == 0) {   // EPQ of layer 0 was overwritten by layer 1: recompute from h^0
       const int bad = epq_phase(g, hin, sW + S_WPQT0, sW + S_B0);
       exact = __syncthreads_or(bad);
+      UPB_STAMP(17);
     }
     const bool last = (l == 1);
     const float4 ce4 = last ? ld4(sV + V_CE + q * 4) : f4(0.f);
     const bool use_head = last && g.stage == 0;
     const float4 bsum = exact ? pull_backward<true>(g, q, ce4, use_head) : pull_backward<false>(g, q, ce4, use_head);
     block_sum_q4(bsum, sRed, sV + V_TMP16);     // barriers inside: GPQ complete, EPQ dead
+    UPB_STAMP(15+(1-l)*3);
     if (tid < 16) gacc(gp, (l == 0 ? P_GCN0_B : P_GCN1_B) + tid, sV[V_TMP16 + tid]);
-    {   // g_W[o][c] = sum_i GPQ[i][o] h^l[i][c]: 4x4 register tiles, K split over the 16 warps
-      float* redbuf = smem + S_EPQ;              // [NW][512]
+    if (warp < KW) {   // g_W[o][c] = sum_i GPQ[i][o] h^l[i][c]: 4x4 register tiles, K split over KW warps
+      float* redbuf = smem + S_EPQ;              // [KW][512]
       const int to = lane >> 2, tc = lane & 3;
       float acc[4][4];
 #pragma unroll
       for (int x = 0; x < 4; ++x)
 #pragma unroll
         for (int y = 0; y < 4; ++y) acc[x][y] = 0.f;
-      for (int i = warp; i < n; i += NW) {
+      for (int i = warp; i < n; i += KW) {
         const float4 gq = ld4(g.GPQ + i * 32 + to * 4);
         const float4 hv = *reinterpret_cast<const float4*>(hin + (size_t)i * 16 + tc * 4);
 #pragma unroll
@@ -1038,16 +1067,17 @@ __device__ void graph_body(const StepArgs& a, const BlobHeader& hd, const GraphD
       st4(g.H + i * 16 + q * 4, s);
     }
     __syncthreads();
-    {
+    if (tid < 512) {
       const float* redbuf = smem + S_EPQ;
       float s = 0.f;
 #pragma unroll
-      for (int w = 0; w < NW; ++w) s += redbuf[w * 512 + tid];
+      for (int w = 0; w < KW; ++w) s += redbuf[w * 512 + tid];
       const int o = tid >> 4, c = tid & 15;
       const int dst = o < 16 ? o * 32 + c : (o - 16) * 32 + 16 + c;
       gacc(gp, (l == 0 ? P_GCN0_W : P_GCN1_W) + dst, s);
     }
     __syncthreads();
+    UPB_STAMP(16+(1-l)*3);
   }
 
   // ---- node encoder backward: g_We = g_h0^T X + g_hc x_cur^T, g_be = sum g_h0 + g_hc
@@ -1089,6 +1119,7 @@ __device__ void graph_body(const StepArgs& a, const BlobHeader& hd, const GraphD
     if (tid < 16) gacc(gp, P_ENC_B + tid, sV[V_TMP16 + tid] + sV[V_GHC + tid]);
   }
   __syncthreads();
+  UPB_STAMP(21);
 }
 
 template <bool TRAIN>
@@ -1117,8 +1148,8 @@ __global__ void __launch_bounds__(NT, 1) k_sgnn(const __grid_constant__ StepArgs
       continue;
     }
     const bool big = d.n > NS || 2 * d.e > AS || d.k > KS;
-    if (big) graph_body<TRAIN, true>(a, hd, d, gid, smem, gp, scr);
-    else graph_body<TRAIN, false>(a, hd, d, gid, smem, gp, scr);
+    if (big) graph_body<TRAIN, true>(a, hd, d, gid, smem, gp, scr, item == (int)blockIdx.x);
+    else graph_body<TRAIN, false>(a, hd, d, gid, smem, gp, scr, item == (int)blockIdx.x);
     __syncthreads();
   }
 }

@@ -33,6 +33,7 @@ struct upb_ctx {
   float* host_pinned = nullptr; // [UPB_STAT_COUNT] pinned staging for upb_read_losses
   int64_t launches = 0;
   bool profiling = false;
+  long long* stamps = nullptr;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
   size_t prof_used = 0;
 };
@@ -108,6 +109,7 @@ StepArgs base_args(upb_ctx* ctx, const void* blob, const int32_t* ids, int count
   a.scratch_stride = ctx->scratch_stride;
   a.n_cap = ctx->cfg.n_cap;
   a.e_cap = ctx->cfg.e_cap;
+  a.stamps = ctx->stamps;
   return a;
 }
 
@@ -325,6 +327,12 @@ extern "C" int upb_profile_read(upb_ctx* ctx, double* total_ms, int* launches) {
   if (total_ms) *total_ms = tot;
   if (launches) *launches = (int)ctx->prof_used;
   ctx->prof_used = 0;
+  return UPB_OK;
+}
+
+extern "C" int upb_set_stamp_buffer(upb_ctx* ctx, void* stamps_dev) {
+  if (int rc = check_ctx(ctx, "set_stamp_buffer")) return rc;
+  ctx->stamps = (long long*)stamps_dev;
   return UPB_OK;
 }
 

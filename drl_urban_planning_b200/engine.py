@@ -147,6 +147,10 @@ class Engine:
         _lib.check(_lib.lib().upb_profile_read(self._ctx, C.byref(ms), C.byref(n)), "upb_profile_read")
         return float(ms.value), int(n.value)
 
+    def set_stamp_buffer(self, buf: Optional[torch.Tensor]) -> None:
+        """int64[64] device tensor receiving clock64() phase stamps (debug), or None."""
+        _lib.check(_lib.lib().upb_set_stamp_buffer(self._ctx, _ptr(buf)), "upb_set_stamp_buffer")
+
     @property
     def launches(self) -> int:
         return int(_lib.lib().upb_launch_count(self._ctx))

@@ -1,0 +1,37 @@
+#!/usr/bin/env python
+"""Cycle budget of the fused kernel's phases for one HLG graph (CTA 0, first graph): python tools/phase_times.py"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from drl_urban_planning_b200 import params as PL, synth
+from drl_urban_planning_b200.engine import Engine
+from drl_urban_planning_b200.packing import pack_states
+
+NAMES = {1: "setup (stage lists, inv)", 2: "h0 + numeric L0", 3: "epq L0", 4: "pull fwd L0", 5: "epq L1", 6: "pull fwd L1 + means",
+         7: "attention fwd", 8: "value head fwd", 9: "policy head fwd", 10: "softmax + outputs", 11: "seeds + g_z",
+         12: "policy head bwd", 13: "value + numeric bwd", 14: "attention bwd", 15: "pull bwd L1", 16: "gW/g_h L1",
+         17: "epq L0 (recompute)", 18: "pull bwd L0", 19: "gW/g_h L0", 21: "node encoder bwd"}
+dev = torch.device("cuda", 0)
+count = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+states, actions = synth.make_states(111, "hlg", count)
+blob = pack_states(states).to(dev)
+eng = Engine(dev, blob.n_cap, blob.e_cap)
+t = lambda x: torch.as_tensor(x, device=dev)
+adv, ret, exps = synth.make_ppo_targets(1, count)
+fixed = np.full((count, 1), -4.0, np.float32)
+params = t(PL.default_init(1))
+stamps = torch.zeros(64, dtype=torch.int64, device=dev)
+args = (blob, params, t(actions), t(adv), t(ret), t(fixed), t(exps), 1.0 / count, 1.0 / count)
+for _ in range(3):
+    eng.ppo_grad(*args)
+eng.set_stamp_buffer(stamps)
+eng.ppo_grad(*args)
+torch.cuda.synchronize()
+st = stamps.cpu().numpy()
+print("graph 0: n, e, k, stage =", blob.info[0])
+prev, tot = st[0], st[21] - st[0]
+for i in range(1, 22):
+    if st[i] == 0: continue
+    print(f"{i:3d} {NAMES.get(i, ''):28s} {st[i] - prev:8d} cycles  {100.0 * (st[i] - prev) / tot:5.1f}%")
+    prev = st[i]
+print("total", tot, "cycles")
