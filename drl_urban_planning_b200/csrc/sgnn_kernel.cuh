@@ -367,62 +367,75 @@ struct GraphView {
 };
 
 // exp-transformed edge-MLP pre-activations of one layer: EPQ[i][o] = exp(2 (Wpq[o] . h_i + b[o]))  (b only for o<16).
-// 8 lanes per node PAIR, 4 outputs per lane; WT is the [16 c][32 o] transpose so a quarter-warp reads 128
-// contiguous bytes (no bank conflicts) and every weight vector is reused for two nodes.
+// 8 lanes per node PAIR, 4 outputs per lane.  Each lane keeps its 16x4 slice of the transposed weights WT[c][o] in
+// registers for the whole phase (64 floats), so a pair costs only the 8 row loads of the two h vectors.
 __device__ __forceinline__ int epq_phase(const GraphView& g, const float* hsrc, const float* WT, const float* b) {
   const int og = threadIdx.x & 7;
   const float4 bias = og < 4 ? ld4(b + og * 4) : f4(0.f);
+  float2 wlo[16], whi[16];
+#pragma unroll
+  for (int c = 0; c < 16; ++c) {
+    const float4 w = ld4(WT + c * 32 + og * 4);
+    wlo[c] = make_float2(w.x, w.y); whi[c] = make_float2(w.z, w.w);
+  }
   const int npair = (g.n + 1) >> 1;
   float amax = 0.f;
   for (int task = threadIdx.x; task < npair * 8; task += NT) {
     const int i0 = (task >> 3) * 2;
     const int i1 = min(i0 + 1, g.n - 1);
-    float ha[16], hb[16];
+    float4 ha[4], hb[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float4 a = ld4(hsrc + i0 * 16 + j * 4), c = ld4(hsrc + i1 * 16 + j * 4);
-      ha[j * 4] = a.x; ha[j * 4 + 1] = a.y; ha[j * 4 + 2] = a.z; ha[j * 4 + 3] = a.w;
-      hb[j * 4] = c.x; hb[j * 4 + 1] = c.y; hb[j * 4 + 2] = c.z; hb[j * 4 + 3] = c.w;
-    }
-    float4 sa = bias, sb = bias;
+    for (int j = 0; j < 4; ++j) { ha[j] = ld4(hsrc + i0 * 16 + j * 4); hb[j] = ld4(hsrc + i1 * 16 + j * 4); }
+    float2 a0 = make_float2(bias.x, bias.y), a1 = make_float2(bias.z, bias.w), b0 = a0, b1 = a1;
 #pragma unroll
     for (int c = 0; c < 16; ++c) {
-      const float4 w = ld4(WT + c * 32 + og * 4);
-      sa.x = fmaf(w.x, ha[c], sa.x); sa.y = fmaf(w.y, ha[c], sa.y); sa.z = fmaf(w.z, ha[c], sa.z); sa.w = fmaf(w.w, ha[c], sa.w);
-      sb.x = fmaf(w.x, hb[c], sb.x); sb.y = fmaf(w.y, hb[c], sb.y); sb.z = fmaf(w.z, hb[c], sb.z); sb.w = fmaf(w.w, hb[c], sb.w);
+      const float xa = comp(ha[c >> 2], c & 3), xb = comp(hb[c >> 2], c & 3);
+      const float2 xa2 = make_float2(xa, xa), xb2 = make_float2(xb, xb);
+      a0 = __ffma2_rn(wlo[c], xa2, a0); a1 = __ffma2_rn(whi[c], xa2, a1);
+      b0 = __ffma2_rn(wlo[c], xb2, b0); b1 = __ffma2_rn(whi[c], xb2, b1);
     }
-    amax = fmaxf(amax, fmaxf(fmaxf(fabsf(sa.x), fabsf(sa.y)), fmaxf(fabsf(sa.z), fabsf(sa.w))));
-    amax = fmaxf(amax, fmaxf(fmaxf(fabsf(sb.x), fabsf(sb.y)), fmaxf(fabsf(sb.z), fabsf(sb.w))));
-    st4(g.EPQ + i0 * 32 + og * 4, make_float4(exp2a(sa.x), exp2a(sa.y), exp2a(sa.z), exp2a(sa.w)));
-    if (i1 != i0) st4(g.EPQ + i1 * 32 + og * 4, make_float4(exp2a(sb.x), exp2a(sb.y), exp2a(sb.z), exp2a(sb.w)));
+    amax = fmaxf(amax, fmaxf(fmaxf(fabsf(a0.x), fabsf(a0.y)), fmaxf(fabsf(a1.x), fabsf(a1.y))));
+    amax = fmaxf(amax, fmaxf(fmaxf(fabsf(b0.x), fabsf(b0.y)), fmaxf(fabsf(b1.x), fabsf(b1.y))));
+    st4(g.EPQ + i0 * 32 + og * 4, make_float4(exp2a(a0.x), exp2a(a0.y), exp2a(a1.x), exp2a(a1.y)));
+    if (i1 != i0) st4(g.EPQ + i1 * 32 + og * 4, make_float4(exp2a(b0.x), exp2a(b0.y), exp2a(b1.x), exp2a(b1.y)));
   }
   return !(amax <= 10.9f);      // also true for NaN
 }
+
+// Bank-conflict-free row access for the pulls.  An EPQ row is 32 floats: EP in banks 0-15, EQ in banks 16-31.  A
+// 128-bit shared load is served per quarter-warp (8 lanes = two 4-lane node groups); if both groups read the EP half
+// of their neighbour rows they collide.  So the odd group of every pair reads the halves in the opposite order:
+//   X = row[offX..], Y = row[offY..] with (offX, offY) = odd ? (16, 0) : (0, 16), and the node's own factors are
+//   swapped to match, m1 = A X + 1, m2 = B Y + 1 with (A, B) = odd ? (EP_i, EQ_i) : (EQ_i, EP_i).
+// {m1, m2} = {a, b} = {EP_i EQ_k + 1, EP_k EQ_i + 1}: the forward is symmetric in them; the backward un-swaps its
+// two accumulators once per node.
 
 // one GCN layer forward, in place: H[i] += (sum over the CSR row of he(i,k)) / (deg_i + eps).  4 lanes per node.
 template <bool EXACT>
 __device__ __forceinline__ void pull_forward(const GraphView& g, int q, bool save_h1, float* h1g, bool want_sums,
                                              float4& msum, float4& hsum) {
+  const int odd = (threadIdx.x >> 2) & 1;
+  const int offX = (odd ? 16 : 0) + q * 4, offY = (odd ? 0 : 16) + q * 4;
   for (int task = threadIdx.x; task < g.n * 4; task += NT) {
     const int i = g.ord[task >> 2];
-    const F2x2 epi = ldp(g.EPQ + i * 32 + q * 4), eqi = ldp(g.EPQ + i * 32 + 16 + q * 4);
+    const F2x2 A = ldp(g.EPQ + i * 32 + offY), B = ldp(g.EPQ + i * 32 + offX);
     const int beg = g.rp[i], end = g.rp[i + 1];
     float2 s0 = make_float2(0.f, 0.f), s1 = s0, s2 = s0, s3 = s0;
     int t = beg;
     for (; t + 1 < end; t += 2) {       // two neighbours per trip: four independent dependency chains
       const int k0 = g.adj[t] & 0xffffu, k1 = g.adj[t + 1] & 0xffffu;
-      const F2x2 ep0 = ldp(g.EPQ + k0 * 32 + q * 4), eq0 = ldp(g.EPQ + k0 * 32 + 16 + q * 4);
-      const F2x2 ep1 = ldp(g.EPQ + k1 * 32 + q * 4), eq1 = ldp(g.EPQ + k1 * 32 + 16 + q * 4);
-      fwd_term<EXACT>(epi.a, eqi.a, ep0.a, eq0.a, s0);
-      fwd_term<EXACT>(epi.b, eqi.b, ep0.b, eq0.b, s1);
-      fwd_term<EXACT>(epi.a, eqi.a, ep1.a, eq1.a, s2);
-      fwd_term<EXACT>(epi.b, eqi.b, ep1.b, eq1.b, s3);
+      const F2x2 X0 = ldp(g.EPQ + k0 * 32 + offX), Y0 = ldp(g.EPQ + k0 * 32 + offY);
+      const F2x2 X1 = ldp(g.EPQ + k1 * 32 + offX), Y1 = ldp(g.EPQ + k1 * 32 + offY);
+      fwd_term<EXACT>(A.a, B.a, Y0.a, X0.a, s0);
+      fwd_term<EXACT>(A.b, B.b, Y0.b, X0.b, s1);
+      fwd_term<EXACT>(A.a, B.a, Y1.a, X1.a, s2);
+      fwd_term<EXACT>(A.b, B.b, Y1.b, X1.b, s3);
     }
     if (t < end) {
       const int k0 = g.adj[t] & 0xffffu;
-      const F2x2 ep0 = ldp(g.EPQ + k0 * 32 + q * 4), eq0 = ldp(g.EPQ + k0 * 32 + 16 + q * 4);
-      fwd_term<EXACT>(epi.a, eqi.a, ep0.a, eq0.a, s0);
-      fwd_term<EXACT>(epi.b, eqi.b, ep0.b, eq0.b, s1);
+      const F2x2 X0 = ldp(g.EPQ + k0 * 32 + offX), Y0 = ldp(g.EPQ + k0 * 32 + offY);
+      fwd_term<EXACT>(A.a, B.a, Y0.a, X0.a, s0);
+      fwd_term<EXACT>(A.b, B.b, Y0.b, X0.b, s1);
     }
     const float cnt = (float)(end - beg);
     const float4 acc = make_float4(cnt - (s0.x + s2.x), cnt - (s0.y + s2.y), cnt - (s1.x + s3.x), cnt - (s1.y + s3.y));
@@ -435,38 +448,65 @@ __device__ __forceinline__ void pull_forward(const GraphView& g, int q, bool sav
   }
 }
 
-// one GCN layer backward (pull): GPQ[i] = (gP_i | gQ_i) from g_h' (in H), EPQ and, on the last layer, the mean /
-// head gradients of the edge activations.  Returns this thread's share of sum_i gP_i (bias gradient).
+// one GCN layer backward (pull).  H holds the SCALED incoming gradient gs_i = g_h'_i / (deg_i + eps); writes
+// GPQ[i] = (gP_i | gQ_i) using EPQ and, on the last layer, the mean / head gradients of the edge activations.
+// Returns this thread's share of sum_i gP_i (bias gradient).
 template <bool EXACT>
 __device__ __forceinline__ float4 pull_backward(const GraphView& g, int q, float4 ce4, bool use_head) {
   float4 bsum = f4(0.f);
   const float2 two = make_float2(2.f, 2.f);
+  const int odd = (threadIdx.x >> 2) & 1;
+  const int offX = (odd ? 16 : 0) + q * 4, offY = (odd ? 0 : 16) + q * 4;
   for (int task = threadIdx.x; task < g.n * 4; task += NT) {
     const int i = g.ord[task >> 2];
-    const F2x2 epi = ldp(g.EPQ + i * 32 + q * 4), eqi = ldp(g.EPQ + i * 32 + 16 + q * 4);
-    const float4 gsi4 = (ld4(g.H + i * 16 + q * 4) * g.inv[i] + ce4) * 2.f;     // 2 (g_h'_i/(deg_i+eps) + g_me/e)
+    const F2x2 A = ldp(g.EPQ + i * 32 + offY), B = ldp(g.EPQ + i * 32 + offX);
+    const float4 gsi4 = (ld4(g.H + i * 16 + q * 4) + ce4) * 2.f;                  // 2 (gs_i + g_me/e)
     const float2 gsa = make_float2(gsi4.x, gsi4.y), gsb = make_float2(gsi4.z, gsi4.w);
     const int beg = g.rp[i], end = g.rp[i + 1];
-    float2 pa = make_float2(0.f, 0.f), pb = pa, qa = pa, qb = pa;
-    for (int t = beg; t < end; ++t) {
-      const uint32_t ent = g.adj[t];
-      const int k = ent & 0xffffu;
-      const F2x2 epk = ldp(g.EPQ + k * 32 + q * 4), eqk = ldp(g.EPQ + k * 32 + 16 + q * 4);
-      const F2x2 hk = ldp(g.H + k * 16 + q * 4);
-      const float iv2 = 2.f * g.inv[k];
-      const float2 iv22 = make_float2(iv2, iv2);
-      float2 gea = __ffma2_rn(hk.a, iv22, gsa), geb = __ffma2_rn(hk.b, iv22, gsb);
-      if (use_head && (ent >> 16)) {
-        const F2x2 gh = ldp(g.ghead + (size_t)((ent >> 16) - 1) * 16 + q * 4);
-        gea = __ffma2_rn(gh.a, two, gea);
-        geb = __ffma2_rn(gh.b, two, geb);
+    float2 u0 = make_float2(0.f, 0.f), u1 = u0, v0 = u0, v1 = u0;    // u: terms of m1, v: terms of m2
+    float2 w0 = u0, w1 = u0, z0 = u0, z1 = u0;                      // second chain (odd entries)
+    int t = beg;
+    for (; t + 1 < end; t += 2) {
+      const uint32_t e0 = g.adj[t], e1 = g.adj[t + 1];
+      const int k0 = e0 & 0xffffu, k1 = e1 & 0xffffu;
+      const F2x2 X0 = ldp(g.EPQ + k0 * 32 + offX), Y0 = ldp(g.EPQ + k0 * 32 + offY), h0 = ldp(g.H + k0 * 16 + q * 4);
+      const F2x2 X1 = ldp(g.EPQ + k1 * 32 + offX), Y1 = ldp(g.EPQ + k1 * 32 + offY), h1 = ldp(g.H + k1 * 16 + q * 4);
+      float2 ga0 = __ffma2_rn(h0.a, two, gsa), gb0 = __ffma2_rn(h0.b, two, gsb);
+      float2 ga1 = __ffma2_rn(h1.a, two, gsa), gb1 = __ffma2_rn(h1.b, two, gsb);
+      if (use_head) {
+        if (e0 >> 16) {
+          const F2x2 gh = ldp(g.ghead + (size_t)((e0 >> 16) - 1) * 16 + q * 4);
+          ga0 = __ffma2_rn(gh.a, two, ga0); gb0 = __ffma2_rn(gh.b, two, gb0);
+        }
+        if (e1 >> 16) {
+          const F2x2 gh = ldp(g.ghead + (size_t)((e1 >> 16) - 1) * 16 + q * 4);
+          ga1 = __ffma2_rn(gh.a, two, ga1); gb1 = __ffma2_rn(gh.b, two, gb1);
+        }
       }
-      bwd_term<EXACT>(epi.a, eqi.a, epk.a, eqk.a, gea, pa, qa);
-      bwd_term<EXACT>(epi.b, eqi.b, epk.b, eqk.b, geb, pb, qb);
+      bwd_term<EXACT>(A.a, B.a, Y0.a, X0.a, ga0, u0, v0);
+      bwd_term<EXACT>(A.b, B.b, Y0.b, X0.b, gb0, u1, v1);
+      bwd_term<EXACT>(A.a, B.a, Y1.a, X1.a, ga1, w0, z0);
+      bwd_term<EXACT>(A.b, B.b, Y1.b, X1.b, gb1, w1, z1);
     }
-    const float4 aP = make_float4(pa.x, pa.y, pb.x, pb.y);
+    if (t < end) {
+      const uint32_t e0 = g.adj[t];
+      const int k0 = e0 & 0xffffu;
+      const F2x2 X0 = ldp(g.EPQ + k0 * 32 + offX), Y0 = ldp(g.EPQ + k0 * 32 + offY), h0 = ldp(g.H + k0 * 16 + q * 4);
+      float2 ga0 = __ffma2_rn(h0.a, two, gsa), gb0 = __ffma2_rn(h0.b, two, gsb);
+      if (use_head && (e0 >> 16)) {
+        const F2x2 gh = ldp(g.ghead + (size_t)((e0 >> 16) - 1) * 16 + q * 4);
+        ga0 = __ffma2_rn(gh.a, two, ga0); gb0 = __ffma2_rn(gh.b, two, gb0);
+      }
+      bwd_term<EXACT>(A.a, B.a, Y0.a, X0.a, ga0, u0, v0);
+      bwd_term<EXACT>(A.b, B.b, Y0.b, X0.b, gb0, u1, v1);
+    }
+    // bwd_term(epi:=A, eqi:=B, epk:=Y, eqk:=X): first accumulator <- terms of A X + 1, second <- terms of Y B + 1.
+    // odd group:  A X = EP_i EQ_k (= a -> gP),  Y B = EP_k EQ_i (= b -> gQ);   even group: the other way round.
+    const float4 t1 = make_float4(u0.x + w0.x, u0.y + w0.y, u1.x + w1.x, u1.y + w1.y);
+    const float4 t2 = make_float4(v0.x + z0.x, v0.y + z0.y, v1.x + z1.x, v1.y + z1.y);
+    const float4 aP = odd ? t1 : t2, aQ = odd ? t2 : t1;
     st4(g.GPQ + i * 32 + q * 4, aP);
-    st4(g.GPQ + i * 32 + 16 + q * 4, make_float4(qa.x, qa.y, qb.x, qb.y));
+    st4(g.GPQ + i * 32 + 16 + q * 4, aQ);
     bsum = bsum + aP;
   }
   return bsum;
@@ -974,7 +1014,7 @@ __device__ void graph_body(const StepArgs& a, const BlobHeader& hd, const GraphD
         const float gs = ai * (dp - gdot);
         gsh = gsh + h * gs;
         // g_h^L = g_mean/n + a_i g_hbar (value path) + g_s qk (key path); in place over h^L
-        st4(g.H + i * 16 + q * 4, gmn4 + gh4 * ai + qk4 * gs);
+        st4(g.H + i * 16 + q * 4, (gmn4 + gh4 * ai + qk4 * gs) * g.inv[i]);   // stored scaled by 1/(deg+eps)
       }
     }
     block_sum_q4(gsh, sRed, sV + V_GSH);
@@ -1005,7 +1045,8 @@ __device__ void graph_body(const StepArgs& a, const BlobHeader& hd, const GraphD
   if (g.stage == 1) {   // road head feeds h^L of its candidate nodes directly
     for (int task = tid; task < k * 16; task += NT) {
       const int j = task >> 4, c = task & 15;
-      g.H[(int)g.cuv[j] * 16 + c] += g.ghead[(size_t)j * 16 + c];
+      const int node = (int)g.cuv[j];
+      g.H[node * 16 + c] += g.ghead[(size_t)j * 16 + c] * g.inv[node];
     }
   }
   __syncthreads();
@@ -1036,35 +1077,59 @@ __device__ void graph_body(const StepArgs& a, const BlobHeader& hd, const GraphD
       for (int x = 0; x < 4; ++x)
 #pragma unroll
         for (int y = 0; y < 4; ++y) acc[x][y] = 0.f;
-      for (int i = warp; i < n; i += KW) {
-        const float4 gq = ld4(g.GPQ + i * 32 + to * 4);
-        const float4 hv = *reinterpret_cast<const float4*>(hin + (size_t)i * 16 + tc * 4);
+      for (int i = warp; i < n; i += 4 * KW) {   // four nodes per trip: their global h rows are in flight together
+        float4 gq[4], hv[4];
 #pragma unroll
-        for (int x = 0; x < 4; ++x) {
-          const float gx = comp(gq, x);
-          acc[x][0] = fmaf(gx, hv.x, acc[x][0]); acc[x][1] = fmaf(gx, hv.y, acc[x][1]);
-          acc[x][2] = fmaf(gx, hv.z, acc[x][2]); acc[x][3] = fmaf(gx, hv.w, acc[x][3]);
+        for (int u = 0; u < 4; ++u) {
+          const int ii = i + u * KW;
+          const bool ok = ii < n;
+          hv[u] = ok ? __ldcg(reinterpret_cast<const float4*>(hin + (size_t)ii * 16 + tc * 4)) : f4(0.f);
+          gq[u] = ok ? ld4(g.GPQ + ii * 32 + to * 4) : f4(0.f);
         }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int x = 0; x < 4; ++x) {
+            const float gx = comp(gq[u], x);
+            acc[x][0] = fmaf(gx, hv[u].x, acc[x][0]); acc[x][1] = fmaf(gx, hv[u].y, acc[x][1]);
+            acc[x][2] = fmaf(gx, hv[u].z, acc[x][2]); acc[x][3] = fmaf(gx, hv[u].w, acc[x][3]);
+          }
       }
 #pragma unroll
       for (int x = 0; x < 4; ++x)
         st4(redbuf + warp * 512 + (to * 4 + x) * 16 + tc * 4, make_float4(acc[x][0], acc[x][1], acc[x][2], acc[x][3]));
     }
-    // g_h = g_h' + GPQ Wpq  (residual), in place
-    for (int task = tid; task < n * 4; task += NT) {
-      const int i = task >> 2;
-      float4 s = ld4(g.H + i * 16 + q * 4);
+    {   // g_h = g_h' + GPQ Wpq (residual), in place.  8 lanes per node pair, 2 output channels per lane; the lane's
+        // 32x2 slice of Wpq lives in registers, so a pair costs the 16 row loads of its two GPQ rows.
+      const int og = tid & 7;
+      float2 w2[32];
 #pragma unroll
-      for (int o4 = 0; o4 < 8; ++o4) {
-        const float4 gq = ld4(g.GPQ + i * 32 + o4 * 4);
+      for (int o = 0; o < 32; ++o) w2[o] = *reinterpret_cast<const float2*>(Wpq + o * 16 + og * 2);
+      const int npair = (n + 1) >> 1;
+      for (int task = tid; task < npair * 8; task += NT) {
+        const int i0 = (task >> 3) * 2, i1 = min(i0 + 1, n - 1);
+        // H holds gs = g_h' / (deg + eps): undo the scaling for the residual term
+        const float rd0 = (float)(g.rp[i0 + 1] - g.rp[i0]) + EPS_DEG, rd1 = (float)(g.rp[i1 + 1] - g.rp[i1]) + EPS_DEG;
+        float2 s0 = *reinterpret_cast<const float2*>(g.H + i0 * 16 + og * 2);
+        float2 s1 = *reinterpret_cast<const float2*>(g.H + i1 * 16 + og * 2);
+        s0.x *= rd0; s0.y *= rd0; s1.x *= rd1; s1.y *= rd1;
 #pragma unroll
-        for (int x = 0; x < 4; ++x) {
-          const float gx = comp(gq, x);
-          const float4 w = ld4(Wpq + (o4 * 4 + x) * 16 + q * 4);
-          s.x = fmaf(gx, w.x, s.x); s.y = fmaf(gx, w.y, s.y); s.z = fmaf(gx, w.z, s.z); s.w = fmaf(gx, w.w, s.w);
+        for (int o4 = 0; o4 < 8; ++o4) {
+          const float4 ga = ld4(g.GPQ + i0 * 32 + o4 * 4), gb = ld4(g.GPQ + i1 * 32 + o4 * 4);
+#pragma unroll
+          for (int x = 0; x < 4; ++x) {
+            const float xa = comp(ga, x), xb = comp(gb, x);
+            s0 = __ffma2_rn(w2[o4 * 4 + x], make_float2(xa, xa), s0);
+            s1 = __ffma2_rn(w2[o4 * 4 + x], make_float2(xb, xb), s1);
+          }
         }
+        if (l == 1) {        // the next (lower) layer's pull wants the scaled form again
+          const float v0 = g.inv[i0], v1 = g.inv[i1];
+          s0.x *= v0; s0.y *= v0; s1.x *= v1; s1.y *= v1;
+        }
+        *reinterpret_cast<float2*>(g.H + i0 * 16 + og * 2) = s0;
+        if (i1 != i0) *reinterpret_cast<float2*>(g.H + i1 * 16 + og * 2) = s1;
       }
-      st4(g.H + i * 16 + q * 4, s);
     }
     __syncthreads();
     if (tid < 512) {
@@ -1090,15 +1155,23 @@ __device__ void graph_body(const StepArgs& a, const BlobHeader& hd, const GraphD
 #pragma unroll
       for (int y = 0; y < 4; ++y) acc[x][y] = 0.f;
     if (lane < 24) {
-      for (int i = warp; i < n; i += NW) {
-        const float4 gh = ld4(g.H + i * 16 + tcc * 4);
-        const float4 xv = __ldg(reinterpret_cast<const float4*>(g.x + (size_t)i * FS) + tf);
+      for (int i = warp; i < n; i += 4 * NW) {   // four nodes per trip: their global feature rows are in flight together
+        float4 gh[4], xv[4];
 #pragma unroll
-        for (int x = 0; x < 4; ++x) {
-          const float gx = comp(gh, x);
-          acc[x][0] = fmaf(gx, xv.x, acc[x][0]); acc[x][1] = fmaf(gx, xv.y, acc[x][1]);
-          acc[x][2] = fmaf(gx, xv.z, acc[x][2]); acc[x][3] = fmaf(gx, xv.w, acc[x][3]);
+        for (int u = 0; u < 4; ++u) {
+          const int ii = i + u * NW;
+          const bool ok = ii < n;
+          xv[u] = ok ? __ldg(reinterpret_cast<const float4*>(g.x + (size_t)ii * FS) + tf) : f4(0.f);
+          gh[u] = ok ? ld4(g.H + ii * 16 + tcc * 4) : f4(0.f);
         }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int x = 0; x < 4; ++x) {
+            const float gx = comp(gh[u], x);
+            acc[x][0] = fmaf(gx, xv[u].x, acc[x][0]); acc[x][1] = fmaf(gx, xv[u].y, acc[x][1]);
+            acc[x][2] = fmaf(gx, xv[u].z, acc[x][2]); acc[x][3] = fmaf(gx, xv[u].w, acc[x][3]);
+          }
       }
 #pragma unroll
       for (int x = 0; x < 4; ++x)
