@@ -198,7 +198,7 @@ def main():
     mb_ids = []
     for m in range(args.pool):
         ids = np.arange(m * BATCH, (m + 1) * BATCH)
-        ids = ids[np.argsort(-cost[ids], kind="stable")]        # longest first: static round-robin over CTAs
+        ids = eng.balance_ids(ids, cost)                        # static schedule: long graph + short graph per CTA
         mb_ids.append(torch.as_tensor(ids.astype(np.int32), device=dev))
     balg_mb = np.array([(1208 * info[m * BATCH:(m + 1) * BATCH, 0] + 42 * info[m * BATCH:(m + 1) * BATCH, 1] + 1300).sum()
                         for m in range(args.pool)], dtype=np.float64)

@@ -54,6 +54,7 @@ _PROTOS = {
     "upb_set_opt_state": (C.c_int, [_VP, _VP, _VP, _VP]),
     "upb_profile_enable": (C.c_int, [_VP, C.c_int]),
     "upb_profile_read": (C.c_int, [_VP, C.POINTER(C.c_double), C.POINTER(C.c_int)]),
+    "upb_grid_size": (C.c_int, [_VP]),
     "upb_set_stamp_buffer": (C.c_int, [_VP, _VP]),
     "upb_launch_count": (C.c_int64, [_VP]),
 }

@@ -138,7 +138,7 @@ int make_plan(int count, const void* const* arrays, int n_cap, int e_cap, int th
     return set_error(UPB_ERR_FORMAT, buf);
   }
   plan->desc.assign(count, GraphDesc{});
-  uint64_t rows = 0, rp = 0, adj = 0, cand = 0, sum_e = 0;
+  uint64_t rows = 0, rp = 0, adj = 0, cand = 0, sum_e = 0, ord = 0;
   for (int i = 0; i < count; ++i) {
     const Counts& c = plan->counts[i];
     GraphDesc& d = plan->desc[i];
@@ -148,6 +148,9 @@ int make_plan(int count, const void* const* arrays, int n_cap, int e_cap, int th
     d.adj_off = (int32_t)adj;
     d.cand_off = (int32_t)cand;
     d.cost = 4 * c.e + c.n + 64;
+    d.ord_off = (int32_t)ord;
+    d.ord_rounds = ((c.n + kPullGroup - 1) / kPullGroup + kPullWarps - 1) / kPullWarps + 1;   // upper bound, see fill_one
+    ord += (uint64_t)d.ord_rounds * kPullWarps * kPullGroup;
     rows += c.n;
     rp += (uint64_t)((c.n + 1 + 7) & ~7);
     adj += (uint64_t)((2 * c.e + 3) & ~3);
@@ -167,7 +170,7 @@ int make_plan(int count, const void* const* arrays, int n_cap, int e_cap, int th
   h.off_num = off;       off = align16(off + (uint64_t)count * kNumDim * sizeof(float));
   h.off_cur = off;       off = align16(off + (uint64_t)count * kNodeStride * sizeof(float));
   h.off_rowptr = off;    off = align16(off + rp * sizeof(uint16_t));
-  h.off_order = off;     off = align16(off + rp * sizeof(uint16_t));
+  h.off_order = off;     off = align16(off + ord * sizeof(uint16_t));
   h.off_adj = off;       off = align16(off + adj * sizeof(uint32_t));
   h.off_cand_uv = off;   off = align16(off + cand * sizeof(uint32_t));
   h.off_cand_idx = off;  off = align16(off + cand * sizeof(int32_t));
@@ -200,13 +203,28 @@ void fill_one(const StateView& s, const GraphDesc& d, const BlobHeader& h, uint8
   for (int i = 0; i < n; ++i) pos[i + 1] += pos[i];
   for (int i = 0; i <= n; ++i) rp[i] = (uint16_t)pos[i];
   for (int i = n + 1; i < ((n + 1 + 7) & ~7); ++i) rp[i] = (uint16_t)pos[n];
-  {  // nodes by descending degree (stable): a warp's 8 nodes then share almost the same trip count in the pull
-    uint16_t* ord = (uint16_t*)(blob + h.off_order) + d.rp_off;
+  {  // Pull schedule.  Nodes sorted by descending degree are cut into groups of 8 (one warp-task: 4 lanes per node,
+     // trip count = the group's largest degree); groups are dealt to the 16 warps longest-first onto the least
+     // loaded warp (LPT), so all warps finish a pull phase at about the same time.
+    uint16_t* ord = (uint16_t*)(blob + h.off_order) + d.ord_off;
+    const int slots = d.ord_rounds * kPullWarps * kPullGroup;
+    for (int i = 0; i < slots; ++i) ord[i] = kNoNode;
     std::vector<int> idx(n);
     for (int i = 0; i < n; ++i) idx[i] = i;
     std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return pos[a + 1] - pos[a] > pos[b + 1] - pos[b]; });
-    for (int i = 0; i < n; ++i) ord[i] = (uint16_t)idx[i];
-    for (int i = n; i < ((n + 1 + 7) & ~7); ++i) ord[i] = 0;
+    const int groups = (n + kPullGroup - 1) / kPullGroup;
+    int load[kPullWarps] = {0}, used[kPullWarps] = {0};
+    for (int gi = 0; gi < groups; ++gi) {
+      const int first = idx[gi * kPullGroup];
+      const int cost = (pos[first + 1] - pos[first] + 1) / 2 + 2;     // trips of two neighbours + fixed overhead
+      int best = -1;
+      for (int w = 0; w < kPullWarps; ++w)
+        if (used[w] < d.ord_rounds && (best < 0 || load[w] < load[best])) best = w;
+      load[best] += cost;
+      const int r = used[best]++;
+      for (int j = 0; j < kPullGroup && gi * kPullGroup + j < n; ++j)
+        ord[(r * kPullWarps + best) * kPullGroup + j] = (uint16_t)idx[gi * kPullGroup + j];
+    }
   }
   int slot = 0;
   for (int j = 0; j < e; ++j) {

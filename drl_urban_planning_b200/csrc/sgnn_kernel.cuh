@@ -110,8 +110,9 @@ constexpr int S_GHEAD = S_GZ + KS;               // [KS][16]
 constexpr int S_CUV = S_GHEAD + KS * 16;         // [KS] u32
 constexpr int S_CIDX = S_CUV + KS;               // [KS] i32
 constexpr int S_RP = S_CIDX + KS;                // [(NS+8)/2] u16 pairs
-constexpr int S_ORD = S_RP + (NS + 8) / 2;       // [(NS+8)/2] u16 pairs: nodes by descending degree
-constexpr int S_ADJ = S_ORD + (NS + 8) / 2;      // [AS] u32
+constexpr int ORD_ROUNDS = ((NS + 7) / 8 + NW - 1) / NW + 1;   // pull-schedule rounds kept in shared memory
+constexpr int S_ORD = S_RP + (NS + 8) / 2;       // [ORD_ROUNDS][NW][8] u16: pull schedule (blob.h)
+constexpr int S_ADJ = S_ORD + ORD_ROUNDS * NW * 4;   // [AS] u32
 constexpr int S_EPQ = S_ADJ + AS;                // [NS][32]
 constexpr int S_GPQ = S_EPQ + NS * 32;           // [NS][32]   (aliased by the head-backward chunk buffers)
 constexpr int S_H = S_GPQ + NS * 32;             // [NS][16]
@@ -120,6 +121,7 @@ constexpr size_t SMEM_BYTES = (size_t)S_TOTAL * 4;
 static_assert(SMEM_BYTES <= 232448, "shared memory budget (227 KB)");
 constexpr int KW = 16;            // warps that share the K dimension of the g_W tile reduction
 static_assert(KW * 512 <= NS * 32 && NW * 384 <= NS * 32, "cross-warp reduction buffers alias the EPQ region");
+static_assert(NW == kPullWarps, "the packer lays the pull schedule out for NT / 32 warps");
 static_assert(NT >= 512 && KW <= NW, "thread (r, c) = (tid >> 4, tid & 15) mappings use the first 512 threads");
 static_assert(CH * (32 + 32 + 16) <= NS * 32, "chunk buffers alias the GPQ region");
 
@@ -360,7 +362,8 @@ struct GraphView {
   float* gz;               // [k]
   float* ghead;            // [k][16]
   const uint16_t* rp;      // [n+1]
-  const uint16_t* ord;     // [n] node ids by descending degree (warp-uniform trip counts in the pull)
+  const uint16_t* ord;     // [ord_rounds][16][8] pull schedule: node ids, 0xFFFF = none (blob.h)
+  int ord_rounds;
   const uint32_t* adj;     // [2e]
   const uint32_t* cuv;     // [k]
   const int* cidx;         // [k]
@@ -416,8 +419,9 @@ __device__ __forceinline__ void pull_forward(const GraphView& g, int q, bool sav
                                              float4& msum, float4& hsum) {
   const int odd = (threadIdx.x >> 2) & 1;
   const int offX = (odd ? 16 : 0) + q * 4, offY = (odd ? 0 : 16) + q * 4;
-  for (int task = threadIdx.x; task < g.n * 4; task += NT) {
+  for (int task = threadIdx.x; task < g.ord_rounds * NT; task += NT) {
     const int i = g.ord[task >> 2];
+    if (i == kNoNode) continue;
     const F2x2 A = ldp(g.EPQ + i * 32 + offY), B = ldp(g.EPQ + i * 32 + offX);
     const int beg = g.rp[i], end = g.rp[i + 1];
     float2 s0 = make_float2(0.f, 0.f), s1 = s0, s2 = s0, s3 = s0;
@@ -457,8 +461,9 @@ __device__ __forceinline__ float4 pull_backward(const GraphView& g, int q, float
   const float2 two = make_float2(2.f, 2.f);
   const int odd = (threadIdx.x >> 2) & 1;
   const int offX = (odd ? 16 : 0) + q * 4, offY = (odd ? 0 : 16) + q * 4;
-  for (int task = threadIdx.x; task < g.n * 4; task += NT) {
+  for (int task = threadIdx.x; task < g.ord_rounds * NT; task += NT) {
     const int i = g.ord[task >> 2];
+    if (i == kNoNode) continue;
     const F2x2 A = ldp(g.EPQ + i * 32 + offY), B = ldp(g.EPQ + i * 32 + offX);
     const float4 gsi4 = (ld4(g.H + i * 16 + q * 4) + ce4) * 2.f;                  // 2 (gs_i + g_me/e)
     const float2 gsa = make_float2(gsi4.x, gsi4.y), gsb = make_float2(gsi4.z, gsi4.w);
@@ -564,7 +569,8 @@ __device__ void graph_body(const StepArgs& a, const BlobHeader& hd, const GraphD
   const float* gnum = reinterpret_cast<const float*>(a.blob + hd.off_num) + (size_t)gid * NUMD;
   const float* gcur = reinterpret_cast<const float*>(a.blob + hd.off_cur) + (size_t)gid * FS;
   const uint16_t* rp_g = reinterpret_cast<const uint16_t*>(a.blob + hd.off_rowptr) + d.rp_off;
-  const uint16_t* ord_g = reinterpret_cast<const uint16_t*>(a.blob + hd.off_order) + d.rp_off;
+  const uint16_t* ord_g = reinterpret_cast<const uint16_t*>(a.blob + hd.off_order) + d.ord_off;
+  g.ord_rounds = d.ord_rounds;
   const uint32_t* adj_g = reinterpret_cast<const uint32_t*>(a.blob + hd.off_adj) + d.adj_off;
   const uint32_t* cuv_g = reinterpret_cast<const uint32_t*>(a.blob + hd.off_cand_uv) + d.cand_off;
   const int* cidx_g = reinterpret_cast<const int*>(a.blob + hd.off_cand_idx) + d.cand_off;
@@ -597,7 +603,7 @@ __device__ void graph_body(const StepArgs& a, const BlobHeader& hd, const GraphD
       for (int i = tid; i < (n + 1 + 7) / 8; i += NT) d0[i] = s0[i];
       const uint4* so = reinterpret_cast<const uint4*>(ord_g);
       uint4* dord = reinterpret_cast<uint4*>(smem + S_ORD);
-      for (int i = tid; i < (n + 7) / 8; i += NT) dord[i] = so[i];
+      for (int i = tid; i < d.ord_rounds * NW; i += NT) dord[i] = so[i];      // 8 node ids (16 bytes) per warp-task
       const uint4* s1 = reinterpret_cast<const uint4*>(adj_g);
       uint4* d1 = reinterpret_cast<uint4*>(adj_s);
       for (int i = tid; i < (2 * e + 3) / 4; i += NT) d1[i] = s1[i];
@@ -1220,7 +1226,7 @@ __global__ void __launch_bounds__(NT, 1) k_sgnn(const __grid_constant__ StepArgs
       }
       continue;
     }
-    const bool big = d.n > NS || 2 * d.e > AS || d.k > KS;
+    const bool big = d.n > NS || 2 * d.e > AS || d.k > KS || d.ord_rounds > ORD_ROUNDS;
     if (big) graph_body<TRAIN, true>(a, hd, d, gid, smem, gp, scr, item == (int)blockIdx.x);
     else graph_body<TRAIN, false>(a, hd, d, gid, smem, gp, scr, item == (int)blockIdx.x);
     __syncthreads();

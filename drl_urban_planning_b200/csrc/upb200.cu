@@ -330,6 +330,8 @@ extern "C" int upb_profile_read(upb_ctx* ctx, double* total_ms, int* launches) {
   return UPB_OK;
 }
 
+extern "C" int upb_grid_size(const upb_ctx* ctx) { return ctx ? ctx->grid : 0; }
+
 extern "C" int upb_set_stamp_buffer(upb_ctx* ctx, void* stamps_dev) {
   if (int rc = check_ctx(ctx, "set_stamp_buffer")) return rc;
   ctx->stamps = (long long*)stamps_dev;

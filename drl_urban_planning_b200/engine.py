@@ -147,6 +147,23 @@ class Engine:
         _lib.check(_lib.lib().upb_profile_read(self._ctx, C.byref(ms), C.byref(n)), "upb_profile_read")
         return float(ms.value), int(n.value)
 
+    @property
+    def grid(self) -> int:
+        return int(_lib.lib().upb_grid_size(self._ctx))
+
+    def balance_ids(self, ids: np.ndarray, cost: np.ndarray) -> np.ndarray:
+        """Order graph ids for the kernel's static schedule (ids[i] -> CTA i % grid, round i // grid): sort by cost,
+        longest first, and reverse every second round so each CTA pairs a long graph with a short one."""
+        ids = np.asarray(ids)
+        order = ids[np.argsort(-np.asarray(cost)[ids], kind="stable")]
+        g = self.grid
+        out = order.copy()
+        for r in range(1, (len(order) + g - 1) // g, 2):
+            seg = order[r * g:(r + 1) * g]
+            # a partial last round is aligned to the END of the CTA range, then reversed: CTA 0 (longest) gets the shortest
+            out[r * g:r * g + len(seg)] = seg[::-1]
+        return out
+
     def set_stamp_buffer(self, buf: Optional[torch.Tensor]) -> None:
         """int64[64] device tensor receiving clock64() phase stamps (debug), or None."""
         _lib.check(_lib.lib().upb_set_stamp_buffer(self._ctx, _ptr(buf)), "upb_set_stamp_buffer")

@@ -146,6 +146,10 @@ int upb_set_opt_state(upb_ctx* ctx, const float* m_host, const float* v_host, co
 int upb_profile_enable(upb_ctx* ctx, int enable);
 int upb_profile_read(upb_ctx* ctx, double* total_ms, int* launches);
 
+/* CTAs the fused kernel is launched with (one per SM unless grid_limit is set).  Graph `ids[i]` of a call is walked by
+ * CTA i % grid in round i / grid, so callers can balance the static schedule (see PPOUpdater.balance_ids). */
+int upb_grid_size(const upb_ctx* ctx);
+
 /* Debug: device int64[64] that receives clock64() stamps at the phase boundaries of the first graph walked by CTA 0
  * of every following fused-kernel launch (NULL switches it off).  See tools/phase_times.py. */
 int upb_set_stamp_buffer(upb_ctx* ctx, void* stamps_dev);

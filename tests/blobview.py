@@ -6,7 +6,7 @@ HEADER = np.dtype([("magic", "<u4"), ("count", "<i4"), ("n_cap", "<i4"), ("e_cap
                    ("off_rowptr", "<u8"), ("off_adj", "<u8"), ("off_cand_uv", "<u8"), ("off_cand_idx", "<u8"),
                    ("sum_n", "<u8"), ("sum_e", "<u8"), ("sum_k", "<u8"), ("off_order", "<u8"), ("reserved", "<u8", (1,))])
 DESC = np.dtype([("n", "<i4"), ("e", "<i4"), ("stage", "<i4"), ("k", "<i4"), ("x_row", "<i4"), ("rp_off", "<i4"),
-                 ("adj_off", "<i4"), ("cand_off", "<i4"), ("cost", "<i4"), ("pad", "<i4", (7,))])
+                 ("adj_off", "<i4"), ("cand_off", "<i4"), ("cost", "<i4"), ("ord_off", "<i4"), ("ord_rounds", "<i4"), ("pad", "<i4", (5,))])
 assert HEADER.itemsize == 128 and DESC.itemsize == 64
 
 

@@ -29,8 +29,17 @@ def check_blob(states, blob):
         adj = d["adj"][g["adj_off"]:g["adj_off"] + 2 * e]
         deg = np.bincount(ei[:e, 0], minlength=n) + np.bincount(ei[:e, 1], minlength=n)
         assert rp[0] == 0 and np.array_equal(np.diff(rp), deg)
-        order = d["order"][g["rp_off"]:g["rp_off"] + n].astype(np.int64)
-        assert sorted(order.tolist()) == list(range(n)) and (np.diff(deg[order]) <= 0).all()
+        sched = d["order"][g["ord_off"]:g["ord_off"] + g["ord_rounds"] * 128].astype(np.int64).reshape(-1, 16, 8)
+        listed = sched[sched != 0xFFFF]
+        assert sorted(listed.tolist()) == list(range(n))            # every node exactly once
+        load = np.zeros(16)
+        for r in range(sched.shape[0]):
+            for w in range(16):
+                grp = sched[r, w][sched[r, w] != 0xFFFF]
+                if grp.size:
+                    load[w] += (deg[grp].max() + 1) // 2 + 2
+        if n >= 256:
+            assert load.max() <= 1.25 * load.mean() + 4, load       # warps are balanced
         # the symmetrised adjacency holds every undirected edge exactly twice (once per endpoint)
         got = sorted((min(i_, int(a & 0xffff)), max(i_, int(a & 0xffff)))
                      for i_ in range(n) for a in adj[rp[i_]:rp[i_ + 1]])
