@@ -32,7 +32,7 @@ constexpr int NW = NT / 32;      // warps per CTA
 constexpr int NS = 464;          // nodes kept in shared memory
 constexpr int AS = 5632;         // directed adjacency entries kept in shared memory
 constexpr int KS = 160;          // action candidates kept in shared memory
-constexpr int CH = 64;           // candidate chunk of the head backward
+constexpr int CH = 96;           // candidate chunk of the head backward
 constexpr float MASK_FILL = -4294967296.0f;   // float32(-2**32 + 1), policy.py:50
 constexpr float EPS_DEG = 1e-6f;               // state_encoder.py:11
 
@@ -60,7 +60,11 @@ constexpr int S_RDB0 = S_RDW0T + 512;      // [32]
 constexpr int S_RDW1 = S_RDB0 + 32;        // [32]
 constexpr int S_WPQT0 = S_RDW1 + 32;       // [16][32]  transpose of S_WPQ0 (bank-conflict-free EPQ phase)
 constexpr int S_WPQT1 = S_WPQT0 + 512;
-constexpr int S_WEND = S_WPQT1 + 512;
+constexpr int S_QCT = S_WPQT1 + 512;       // [16][16] transposes of Qc, Kc, Vc, Wo (conflict-free lane-per-row matvecs)
+constexpr int S_KCT = S_QCT + 256;
+constexpr int S_VCT = S_KCT + 256;
+constexpr int S_WOT = S_VCT + 256;
+constexpr int S_WEND = S_WOT + 256;
 
 // per-graph small vectors
 constexpr int V_X52 = 0;        // [52] numerical features (padded to 56)
@@ -95,10 +99,12 @@ constexpr int V_TMP16 = 1800;   // [16] block-reduce results
 constexpr int V_TMP16B = 1816;  // [16]
 constexpr int V_SC = 1832;      // [24] scalars
 constexpr int V_WEFF = 1856;    // [32][16] Weff (land use), row-major copy for the head backward
-constexpr int V_END = 2368;
+constexpr int V_TMP32 = 2368;   // [32] block-reduce results
+constexpr int V_END = 2400;
 // scalar slots
 constexpr int SC_VALUE = 0, SC_MAX = 1, SC_SUM = 2, SC_LSE = 3, SC_ENT = 4, SC_LOGP = 5, SC_GV = 6, SC_GLP = 7,
-              SC_GH = 8, SC_Z = 9, SC_SLOT = 10, SC_BEST = 11, SC_GDOT = 12;
+              SC_GH = 8, SC_Z = 9, SC_SLOT = 10, SC_BEST = 11, SC_GDOT = 12, SC_ACT = 13, SC_RET = 14, SC_EXP = 15,
+              SC_FLP = 16, SC_ADV = 17, SC_QUEUE = 18;
 
 constexpr int S_VEC = S_WEND;
 constexpr int S_RED = S_VEC + V_END;             // [NW][20] block-reduce scratch
@@ -123,7 +129,26 @@ constexpr int KW = 16;            // warps that share the K dimension of the g_W
 static_assert(KW * 512 <= NS * 32 && NW * 384 <= NS * 32, "cross-warp reduction buffers alias the EPQ region");
 static_assert(NW == kPullWarps, "the packer lays the pull schedule out for NT / 32 warps");
 static_assert(NT >= 512 && KW <= NW, "thread (r, c) = (tid >> 4, tid & 15) mappings use the first 512 threads");
-static_assert(CH * (32 + 32 + 16) <= NS * 32, "chunk buffers alias the GPQ region");
+// GPQ region while it is not holding GPQ (whole forward; backward until the first pull): value-head and numeric-
+// encoder weights (re-staged per graph, padded row strides = conflict-free lane-per-row access), then the policy-head
+// backward buffers.
+constexpr int VN_VW0 = 0;                  // [32][67]   val_w0 (stride 67 is odd: conflict-free both ways)
+constexpr int VN_VB0 = VN_VW0 + 2144;      // [32]
+constexpr int VN_VW1 = VN_VB0 + 32;        // [32][33]   val_w1, row stride 33
+constexpr int VN_VB1 = VN_VW1 + 1056;      // [32]
+constexpr int VN_VW2 = VN_VB1 + 32;        // [32]
+constexpr int VN_VB2 = VN_VW2 + 32;        // [1] (+3 pad)
+constexpr int VN_NW0 = VN_VB2 + 4;         // [64][53]   num_w0, row stride 53
+constexpr int VN_NB0 = VN_NW0 + 3392;      // [64]
+constexpr int VN_NW1 = VN_NB0 + 64;        // [16][65]   num_w1, row stride 65
+constexpr int VN_NB1 = VN_NW1 + 1040;      // [16]
+constexpr int VN_END = VN_NB1 + 16;
+constexpr int HB_GU = (VN_END + 3) & ~3;   // [CH][32] g_u of the chunk's candidates
+constexpr int HB_X = HB_GU + CH * 32;      // [CH][16] head inputs
+constexpr int HB_PGC = HB_X + CH * 16;     // [32 half-warps][32] partial sums of g_u
+constexpr int HB_PGW2 = HB_PGC + 1024;     // [32 half-warps][32] partial sums of g_z t
+constexpr int HB_END = HB_PGW2 + 1024;
+static_assert(HB_END <= NS * 32, "value/numeric weights + head-backward buffers alias the GPQ region");
 
 // per-CTA global scratch (floats): saved layer inputs + big-graph arrays
 __host__ __device__ inline size_t scratch_floats(int n_cap, int e_cap) {
@@ -268,6 +293,56 @@ __device__ __forceinline__ void block_sum_q4(float4 v, float* red, float* out16)
   __syncthreads();
 }
 
+// two float4 partials per thread (channels 4q..4q+3 of two 16-vectors) -> out32[0..15], out32[16..31]
+__device__ __forceinline__ void block_sum_q8(float4 v, float4 w, float* red, float* out32) {
+#pragma unroll
+  for (int o = 4; o < 32; o <<= 1) {
+    v.x += __shfl_xor_sync(0xffffffffu, v.x, o); v.y += __shfl_xor_sync(0xffffffffu, v.y, o);
+    v.z += __shfl_xor_sync(0xffffffffu, v.z, o); v.w += __shfl_xor_sync(0xffffffffu, v.w, o);
+    w.x += __shfl_xor_sync(0xffffffffu, w.x, o); w.y += __shfl_xor_sync(0xffffffffu, w.y, o);
+    w.z += __shfl_xor_sync(0xffffffffu, w.z, o); w.w += __shfl_xor_sync(0xffffffffu, w.w, o);
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane < 4) { st4(red + warp * 20 + lane * 4, v); }
+  __syncthreads();
+  float keep = 0.f;
+  if (threadIdx.x < 16) {
+#pragma unroll
+    for (int x = 0; x < NW; ++x) keep += red[x * 20 + threadIdx.x];
+  }
+  __syncthreads();
+  if (lane < 4) { st4(red + warp * 20 + lane * 4, w); }
+  if (threadIdx.x < 16) out32[threadIdx.x] = keep;
+  __syncthreads();
+  if (threadIdx.x < 16) {
+    float s = 0.f;
+#pragma unroll
+    for (int x = 0; x < NW; ++x) s += red[x * 20 + threadIdx.x];
+    out32[16 + threadIdx.x] = s;
+  }
+  __syncthreads();
+}
+// a float4 partial (channels 4q..) plus one scalar per thread -> out32[0..15], out32[16]
+__device__ __forceinline__ void block_sum_q4p1(float4 v, float sc1, float* red, float* out32) {
+#pragma unroll
+  for (int o = 4; o < 32; o <<= 1) {
+    v.x += __shfl_xor_sync(0xffffffffu, v.x, o); v.y += __shfl_xor_sync(0xffffffffu, v.y, o);
+    v.z += __shfl_xor_sync(0xffffffffu, v.z, o); v.w += __shfl_xor_sync(0xffffffffu, v.w, o);
+  }
+  sc1 = warp_sum(sc1);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane < 4) st4(red + warp * 20 + lane * 4, v);
+  if (lane == 0) red[warp * 20 + 16] = sc1;
+  __syncthreads();
+  if (threadIdx.x < 17) {
+    float s = 0.f;
+#pragma unroll
+    for (int x = 0; x < NW; ++x) s += red[x * 20 + threadIdx.x];
+    out32[threadIdx.x] = s;
+  }
+  __syncthreads();
+}
+
 // y[row] = act(b[row] + W[row][:] . x) for row < rows; 8 lanes per row; rows must be a multiple of 4.
 // W, b in global memory (read through L1/L2), x and y in shared memory.  No barrier inside.
 template <bool TANH>
@@ -323,6 +398,11 @@ __device__ __forceinline__ void load_weights(const float* __restrict__ P, float*
     sW[S_KC + i] = k;
     sW[S_VC + i] = v;
     sW[S_WO + i] = P[P_MHA_OUT_W + i];
+    const int tr = c * 16 + r;
+    sW[S_QCT + tr] = q;
+    sW[S_KCT + tr] = k;
+    sW[S_VCT + tr] = v;
+    sW[S_WOT + tr] = P[P_MHA_OUT_W + i];
   }
   if (t < 16) {
     float q = P[P_MHA_IN_B + t], v = P[P_MHA_IN_B + 32 + t];
@@ -546,6 +626,309 @@ __device__ __forceinline__ void gacc(float* gp, int idx, float v) {
   asm volatile("red.global.add.f32 [%0], %1;" ::"l"(gp + idx), "f"(v) : "memory");
 }
 
+
+// ---- small dense blocks run by single warps from shared-memory weights ------------------------------------------
+// value-head and numeric-encoder weights -> the (currently free) GPQ region, with padded row strides
+__device__ __forceinline__ void stage_vn_weights(const float* __restrict__ P, float* vn) {
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  for (int i = t; i < HID * SVD; i += NT) vn[VN_VW0 + i] = __ldg(P + P_VAL_W0 + i);       // same [32][67] layout
+  for (int i = t; i < HID * HID; i += NT) vn[VN_VW1 + (i >> 5) * 33 + (i & 31)] = __ldg(P + P_VAL_W1 + i);
+  for (int u = warp; u < NH0; u += NW) {                                                  // [64][52] -> row stride 53
+    vn[VN_NW0 + u * 53 + lane] = __ldg(P + P_NUM_W0 + u * NUMD + lane);
+    if (lane < NUMD - 32) vn[VN_NW0 + u * 53 + 32 + lane] = __ldg(P + P_NUM_W0 + u * NUMD + 32 + lane);
+  }
+  for (int i = t; i < 16 * NH0; i += NT) vn[VN_NW1 + (i >> 6) * 65 + (i & 63)] = __ldg(P + P_NUM_W1 + i);
+  if (t < 32) {
+    vn[VN_VB0 + t] = __ldg(P + P_VAL_B0 + t);
+    vn[VN_VB1 + t] = __ldg(P + P_VAL_B1 + t);
+    vn[VN_VW2 + t] = __ldg(P + P_VAL_W2 + t);
+  }
+  if (t >= 32 && t < 96) vn[VN_NB0 + t - 32] = __ldg(P + P_NUM_B0 + t - 32);
+  if (t >= 96 && t < 112) vn[VN_NB1 + t - 96] = __ldg(P + P_NUM_B1 + t - 96);
+  if (t == 112) vn[VN_VB2] = __ldg(P + P_VAL_B2);
+}
+
+__device__ __forceinline__ void group_bar(int id, int nthreads) {      // named barrier of a warp group
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// numeric feature encoder (state_encoder.py:35-57,187).  Layer 0: warps 0,1 (one hidden unit per lane).
+__device__ __forceinline__ void numeric_l0(const float* vn, const float* x52, float* a0, int warp, int lane) {
+  const int u = warp * 32 + lane;
+  const float* w = vn + VN_NW0 + u * 53;
+  float s0 = vn[VN_NB0 + u], s1 = 0.f;
+#pragma unroll 13
+  for (int k = 0; k < NUMD; k += 2) { s0 = fmaf(w[k], x52[k], s0); s1 = fmaf(w[k + 1], x52[k + 1], s1); }
+  a0[u] = tanhf(s0 + s1);
+}
+// Layer 1: one warp, 16 units x 2 halves of the 64 inputs
+__device__ __forceinline__ void numeric_l1(const float* vn, const float* a0, float* hnum, int lane) {
+  const int r = lane & 15, half = lane >> 4;
+  const float* w = vn + VN_NW1 + r * 65 + half * 32;
+  const float* x = a0 + half * 32;
+  float s0 = 0.f, s1 = 0.f;
+#pragma unroll 16
+  for (int k = 0; k < 32; k += 2) { s0 = fmaf(w[k], x[k], s0); s1 = fmaf(w[k + 1], x[k + 1], s1); }
+  float s = s0 + s1;
+  s += __shfl_xor_sync(0xffffffffu, s, 16);
+  if (lane < 16) hnum[r] = tanhf(s + vn[VN_NB1 + r]);
+}
+
+// Attention tail (hbar, v' = Vc hbar + vbc, att = Wo v' + bo) in one warp's registers; lane & 15 = component.
+// `tmp` holds the block reduction of pass 2: tmp[0..15] = sum_i a_i h_i, tmp[16] = sum_i a_i.
+__device__ __forceinline__ void attention_tail(const float* sW, const float* tmp, int lane, float& hbar, float& vp,
+                                               float& at) {
+  const int c = lane & 15;
+  hbar = tmp[c] / tmp[16];
+  vp = sW[S_VBC + c];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) vp = fmaf(sW[S_VCT + j * 16 + c], __shfl_sync(0xffffffffu, hbar, j), vp);
+  at = sW[S_BO + c];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) at = fmaf(sW[S_WOT + j * 16 + c], __shfl_sync(0xffffffffu, vp, j), at);
+}
+
+// Value head (value.py:15-39) by the 256 threads of warps 0..7: 8 lanes per hidden unit, named barrier 1.
+__device__ __forceinline__ void value_head_group(float* sV, const float* vn, float* sc, int tid) {
+  const int r = tid >> 3, p = tid & 7, lane = tid & 31;
+  {
+    const float* w = vn + VN_VW0 + r * SVD;
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 9; ++j) {
+      const int k = p + 8 * j;
+      if (k < SVD) s = fmaf(w[k], sV[V_SV + k], s);
+    }
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    if (p == 0) sV[V_Y0 + r] = tanhf(s + vn[VN_VB0 + r]);
+  }
+  group_bar(1, 256);
+  {
+    const float* w = vn + VN_VW1 + r * 33;
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) s = fmaf(w[p + 8 * j], sV[V_Y0 + p + 8 * j], s);
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    if (p == 0) sV[V_Y1 + r] = tanhf(s + vn[VN_VB1 + r]);
+  }
+  group_bar(1, 256);
+  if (tid < 32) {
+    const float v = warp_sum(vn[VN_VW2 + lane] * sV[V_Y1 + lane]) + vn[VN_VB2];
+    if (lane == 0) sc[SC_VALUE] = v;
+  }
+}
+
+// Backward of the value head and of the numeric encoder by the 256 threads of warps 0..7 (named barrier 2);
+// leaves g_sv in sV[V_GSV..] and adds the weight gradients to the CTA's gradient row.
+__device__ __forceinline__ void value_numeric_bwd_group(float* sV, const float* vn, float gV, float* gp, int tid) {
+  const int r = tid >> 3, p = tid & 7;
+  if (tid < 32) {
+    const float y1 = sV[V_Y1 + tid];
+    sV[V_D1 + tid] = gV * vn[VN_VW2 + tid] * (1.f - y1 * y1);
+  }
+  group_bar(2, 256);
+  {   // d0[c] = (sum_q W1[q][c] d1[q]) (1 - y0[c]^2): c = r, 8 lanes x 4 q
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) s = fmaf(vn[VN_VW1 + (p + 8 * j) * 33 + r], sV[V_D1 + p + 8 * j], s);
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    const float y0 = sV[V_Y0 + r];
+    if (p == 0) sV[V_D0 + r] = s * (1.f - y0 * y0);
+    // W1 / biases / W2 gradients need d1, y0, y1 only
+#pragma unroll
+    for (int j = 0; j < 4; ++j) gacc(gp, P_VAL_W1 + r * 32 + p + 8 * j, sV[V_D1 + r] * sV[V_Y0 + p + 8 * j]);
+    if (tid < 32) {
+      gacc(gp, P_VAL_B1 + tid, sV[V_D1 + tid]);
+      gacc(gp, P_VAL_W2 + tid, gV * sV[V_Y1 + tid]);
+    }
+    if (tid == 32) gacc(gp, P_VAL_B2, gV);
+  }
+  group_bar(2, 256);
+  if (tid < SVD) {   // g_sv[k] = sum_r W0[r][k] d0[r]
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll 8
+    for (int q = 0; q < 32; q += 2) {
+      s0 = fmaf(vn[VN_VW0 + q * SVD + tid], sV[V_D0 + q], s0);
+      s1 = fmaf(vn[VN_VW0 + (q + 1) * SVD + tid], sV[V_D0 + q + 1], s1);
+    }
+    sV[V_GSV + tid] = s0 + s1;
+  }
+  {   // W0 gradient: row r, columns p, p+8, ...
+    const float d0 = sV[V_D0 + r];
+#pragma unroll
+    for (int j = 0; j < 9; ++j) {
+      const int k = p + 8 * j;
+      if (k < SVD) gacc(gp, P_VAL_W0 + r * SVD + k, d0 * sV[V_SV + k]);
+    }
+    if (tid < 32) gacc(gp, P_VAL_B0 + tid, sV[V_D0 + tid]);
+  }
+  group_bar(2, 256);
+  if (tid < 16) {
+    const float hn = sV[V_SV + tid];
+    sV[V_DN1 + tid] = sV[V_GSV + tid] * (1.f - hn * hn);
+  }
+  group_bar(2, 256);
+  {   // dn0[u] = (sum_r NW1[r][u] dn1[r]) (1 - a0[u]^2): u = tid >> 2 (64 units), 4 lanes x 4 r
+    const int u = tid >> 2, pp = tid & 3;
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) s = fmaf(vn[VN_NW1 + (pp + 4 * j) * 65 + u], sV[V_DN1 + pp + 4 * j], s);
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    const float a0 = sV[V_A0 + u];
+    if (pp == 0) sV[V_DN0 + u] = s * (1.f - a0 * a0);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {          // NW1 gradient: 16 x 64 = 1024 = 256 threads x 4
+      const int idx = tid + 256 * j;
+      gacc(gp, P_NUM_W1 + idx, sV[V_DN1 + (idx >> 6)] * sV[V_A0 + (idx & 63)]);
+    }
+    if (tid < 16) gacc(gp, P_NUM_B1 + tid, sV[V_DN1 + tid]);
+  }
+  group_bar(2, 256);
+  {   // NW0 gradient: unit u = tid >> 2, columns pp, pp+4, ... (52 = 4 x 13)
+    const int u = tid >> 2, pp = tid & 3;
+    const float d = sV[V_DN0 + u];
+#pragma unroll
+    for (int j = 0; j < 13; ++j) gacc(gp, P_NUM_W0 + u * NUMD + pp + 4 * j, d * sV[V_X52 + pp + 4 * j]);
+    if (tid < NH0) gacc(gp, P_NUM_B0 + tid, sV[V_DN0 + tid]);
+  }
+}
+
+// Policy head on one candidate by a HALF-warp: lane c16 owns input channel c16 and hidden units c16, c16 + 16.
+// Returns the two tanh units and the candidate's input channel (he of the edge, or h^L of the node).
+struct HeadLane {
+  float w0[16], w1[16];      // rows c16 and c16+16 of the (effective) first-layer matrix
+  float cb0, cb1, w20, w21;
+  unsigned mask;             // the half-warp's lanes
+};
+__device__ __forceinline__ void head_lane_init(HeadLane& hl, const GraphView& g, const float* sW, const float* sV,
+                                               int lane) {
+  const int c16 = lane & 15;
+  hl.mask = 0xFFFFu << (lane & 16);
+  const float* WT = g.stage == 0 ? sV + V_WEFFT : sW + S_RDW0T;      // [16][32]: conflict-free for lane = unit
+#pragma unroll
+  for (int c = 0; c < 16; ++c) { hl.w0[c] = WT[c * 32 + c16]; hl.w1[c] = WT[c * 32 + c16 + 16]; }
+  if (g.stage == 0) {
+    hl.cb0 = sV[V_CEFF + c16]; hl.cb1 = sV[V_CEFF + c16 + 16];
+    hl.w20 = sW[S_LUW1 + c16]; hl.w21 = sW[S_LUW1 + c16 + 16];
+  } else {
+    hl.cb0 = sW[S_RDB0 + c16]; hl.cb1 = sW[S_RDB0 + c16 + 16];
+    hl.w20 = sW[S_RDW1 + c16]; hl.w21 = sW[S_RDW1 + c16 + 16];
+  }
+}
+__device__ __forceinline__ void head_units(const HeadLane& hl, const GraphView& g, int j, int lane, float& t0, float& t1,
+                                           float& xin) {
+  const int c16 = lane & 15;
+  const uint32_t uv = g.cuv[j];
+  if (g.stage == 0) {
+    const int u = uv & 0xffffu, v = uv >> 16;
+    const float epu = g.EPQ[u * 32 + c16], equ = g.EPQ[u * 32 + 16 + c16];
+    const float epv = g.EPQ[v * 32 + c16], eqv = g.EPQ[v * 32 + 16 + c16];
+    const float r1 = rcp_approx(fmaf(epu, eqv, 1.f)), r2 = rcp_approx(fmaf(epv, equ, 1.f));
+    xin = (1.f - r1) - r2;
+  } else {
+    xin = g.H[(int)uv * 16 + c16];
+  }
+  float p0 = hl.cb0, p1 = hl.cb1;
+#pragma unroll
+  for (int c = 0; c < 16; ++c) {
+    const float x = __shfl_sync(hl.mask, xin, c, 16);
+    p0 = fmaf(hl.w0[c], x, p0);
+    p1 = fmaf(hl.w1[c], x, p1);
+  }
+  t0 = tanhf(p0);
+  t1 = tanhf(p1);
+}
+__device__ __forceinline__ float half_sum(float v, unsigned mask) {
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o, 16);
+  return v;
+}
+
+// One warp: masked softmax over the k candidates (log-softmax over the candidates equals log-softmax over all
+// padded logits: masked entries have probability exactly 0), outputs, PPO seeds and the logit gradients.
+template <bool TRAIN>
+__device__ __forceinline__ void softmax_seeds(const StepArgs& a, const BlobHeader& hd, const GraphView& g, float* sc,
+                                              float* gp, int lane) {
+  const int k = g.k, gid = g.gid;
+  float lmax = -CUDART_INF_F;
+  int lbest = 0x7fffffff;
+  for (int j = lane; j < k; j += 32) {
+    const float zj = g.z[j];
+    if (zj > lmax) { lmax = zj; lbest = j; }     // first index wins inside a lane (j ascending)
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {             // arg-max with first-index tie break (policy.py:72 `probs.argmax`)
+    const float om = __shfl_xor_sync(0xffffffffu, lmax, o);
+    const int ob = __shfl_xor_sync(0xffffffffu, lbest, o);
+    if (om > lmax || (om == lmax && ob < lbest)) { lmax = om; lbest = ob; }
+  }
+  const float zmax = lmax;
+  float lsum = 0.f;
+  for (int j = lane; j < k; j += 32) lsum += expf(g.z[j] - zmax);
+  const float lse = zmax + logf(warp_sum(lsum));
+  const int aidx = a.actions ? (int)sc[SC_ACT] : -1;
+  float lent = 0.f;
+  int slot = -1;
+  for (int j = lane; j < k; j += 32) {
+    const float lp = g.z[j] - lse;
+    lent -= expf(lp) * lp;
+    if (g.cidx[j] == aidx) slot = j;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) slot = max(slot, __shfl_xor_sync(0xffffffffu, slot, o));
+  float H = warp_sum(lent), logp = 0.f;
+  int greedy = 0;
+  if (k > 0) {
+    greedy = g.cidx[lbest];
+    if (a.actions) logp = slot >= 0 ? g.z[slot] - lse : MASK_FILL - lse;
+  } else {      // every logit equals the fill value: uniform over the padded width
+    const float cap = (float)(g.stage == 0 ? hd.e_cap : hd.n_cap);
+    H = logf(cap);
+    if (a.actions) logp = -logf(cap);
+  }
+  const float V = sc[SC_VALUE];
+  if (lane == 0) {
+    sc[SC_LSE] = lse; sc[SC_ENT] = H; sc[SC_LOGP] = logp; sc[SC_SLOT] = (float)(slot + 1);
+    if (a.out_value) a.out_value[gid] = V;
+    if (a.out_logp) a.out_logp[gid] = logp;
+    if (a.out_entropy) a.out_entropy[gid] = H;
+    if (a.out_greedy) a.out_greedy[gid] = greedy;
+  }
+  if constexpr (TRAIN) {
+    const float R = sc[SC_RET], dv = V - R;
+    float glp = 0.f, gH = 0.f, surr = 0.f, negent = 0.f, in_ind = 0.f;
+    if (sc[SC_EXP] != 0.f) {
+      in_ind = 1.f;
+      const float r = expf(logp - sc[SC_FLP]), A = sc[SC_ADV];
+      const float lo = 1.f - a.clip_eps, hi = 1.f + a.clip_eps;
+      const float s1 = r * A, s2 = fminf(fmaxf(r, lo), hi) * A;
+      surr = -fminf(s1, s2);
+      if ((r >= lo && r <= hi) || s1 < s2) glp = -A * r * a.inv_ind;
+      gH = -a.c_entropy * a.inv_ind;
+      negent = -H;
+    }
+    if (lane == 0) {
+      sc[SC_GV] = 2.f * a.c_value * dv * a.inv_batch;
+      float* st = gp + G_STATS;
+      st[0] += dv * dv; st[1] += surr; st[2] += negent; st[3] += 1.f; st[4] += in_ind;
+      st[5] += g.stage == 0 ? 1.f : 0.f; st[6] += g.stage == 1 ? 1.f : 0.f;
+      st[7] += (isfinite(V) && isfinite(logp) && isfinite(H)) ? 0.f : 1.f;
+    }
+    // logits gradient: g_z = g_lp (delta_a - p) - g_H p (logp + H)
+    for (int j = lane; j < k; j += 32) {
+      const float lp = g.z[j] - lse, p = expf(lp);
+      g.gz[j] = glp * ((j == slot ? 1.f : 0.f) - p) - gH * p * (lp + H);
+    }
+  }
+}
+
 #define UPB_STAMP(ID)                                                                      \
   do {                                                                                     \
     if (a.stamps != nullptr && blockIdx.x == 0 && threadIdx.x == 0 && first_item) a.stamps[ID] = clock64(); \
@@ -616,25 +999,38 @@ __device__ void graph_body(const StepArgs& a, const BlobHeader& hd, const GraphD
     g.rp = rp_s; g.adj = adj_s; g.cuv = cuv_s; g.cidx = cidx_s;
     g.ord = reinterpret_cast<const uint16_t*>(smem + S_ORD);
   }
+  float* vn = smem + S_GPQ;          // value-head / numeric-encoder weights live in the idle GPQ region
+  stage_vn_weights(P, vn);
   if (tid < NUMD) sV[V_X52 + tid] = gnum[tid];
   if (tid >= 64 && tid < 64 + FS) sV[V_XCUR + tid - 64] = gcur[tid - 64];
-  if (tid < 24) sc[tid] = 0.f;
+  if (tid >= 96 && tid < 109) sc[tid - 96] = 0.f;
+  if (tid == 109 && a.actions) sc[SC_ACT] = a.actions[(size_t)gid * 2 + g.stage];     // per-graph scalars: fetched early,
+  if constexpr (TRAIN) {                                                             // consumed by the softmax warp
+    if (tid == 110) sc[SC_RET] = a.ret[gid];
+    if (tid == 111) sc[SC_EXP] = a.exps[gid];
+    if (tid == 112) sc[SC_FLP] = a.fixed_lp[gid];
+    if (tid == 113) sc[SC_ADV] = a.adv[gid];
+  }
+  if (tid == 114) reinterpret_cast<int*>(sc)[SC_QUEUE] = 0;
   __syncthreads();
   UPB_STAMP(1);
 
   // ================================================================================ forward
+  if (warp < 2) numeric_l0(vn, sV + V_X52, sV + V_A0, warp, lane);   // numeric encoder, layer 0 (state_encoder.py:35-57)
   for (int i = tid; i < n; i += NT) g.inv[i] = 1.0f / ((float)(g.rp[i + 1] - g.rp[i]) + EPS_DEG);
   // h^0 = X We^T + be (state_encoder.py:189); 4 lanes per node, 4 channels per lane
   for (int task = tid; task < n * 4; task += NT) {
     const int i = task >> 2;
     const float* xr = g.x + (size_t)i * FS;
+    float4 xv[6];
+#pragma unroll
+    for (int f4i = 0; f4i < 6; ++f4i) xv[f4i] = __ldg(reinterpret_cast<const float4*>(xr) + f4i);
     float4 acc = ld4(sW + S_BE + q * 4);
 #pragma unroll
     for (int f4i = 0; f4i < 6; ++f4i) {
-      const float4 xv = __ldg(reinterpret_cast<const float4*>(xr) + f4i);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float xs = comp(xv, j);
+        const float xs = comp(xv[f4i], j);
         const float4 w = ld4(sW + S_WET + (f4i * 4 + j) * 16 + q * 4);
         acc.x = fmaf(w.x, xs, acc.x); acc.y = fmaf(w.y, xs, acc.y);
         acc.z = fmaf(w.z, xs, acc.z); acc.w = fmaf(w.w, xs, acc.w);
@@ -643,16 +1039,30 @@ __device__ void graph_body(const StepArgs& a, const BlobHeader& hd, const GraphD
     st4(g.H + i * 16 + q * 4, acc);
     if (TRAIN) st4(g.H0g + i * 16 + q * 4, acc);
   }
-  if (tid < 16) {   // current node through the same encoder (state_encoder.py:190-191)
-    float s = sW[S_BE + tid];
-    for (int f = 0; f < F; ++f) s = fmaf(sW[S_WET + f * 16 + tid], sV[V_XCUR + f], s);
-    sV[V_HC + tid] = s;
+  if (warp == NW - 1 && lane < 16) {   // current node through the same encoder (state_encoder.py:190-191)
+    float s = sW[S_BE + lane];
+#pragma unroll
+    for (int f = 0; f < F; ++f) s = fmaf(sW[S_WET + f * 16 + lane], sV[V_XCUR + f], s);
+    sV[V_HC + lane] = s;
   }
-  // numeric feature encoder, first layer (state_encoder.py:35-57,187)
-  matvec8<true>(P + P_NUM_W0, P + P_NUM_B0, NH0, NUMD, sV + V_X52, sV + V_A0);
   __syncthreads();
   UPB_STAMP(2);
-  matvec8<true>(P + P_NUM_W1, P + P_NUM_B1, 16, NH0, sV + V_A0, sV + V_SV);
+  if (warp == 0) numeric_l1(vn, sV + V_A0, sV + V_SV, lane);          // numeric encoder, layer 1 -> sv[0..15]
+  if (g.stage == 0 && tid < 512) {
+    // Weff = Wa + Wd + Wc diag(hc), ceff = b + (Wb - Wd) hc   (state_encoder.py:207-210 folded into the head)
+    const int r = tid >> 4, c = tid & 15;
+    const float* w = sW + S_LUW0 + r * 64;
+    const float weff = w[c] + w[48 + c] + w[32 + c] * sV[V_HC + c];
+    sV[V_WEFFT + c * 32 + r] = weff;
+    sV[V_WEFF + r * 16 + c] = weff;
+    if (tid < 32) {
+      const float* wr = sW + S_LUW0 + tid * 64;
+      float s = sW[S_LUB0 + tid];
+#pragma unroll
+      for (int cc = 0; cc < 16; ++cc) s = fmaf(wr[16 + cc] - wr[48 + cc], sV[V_HC + cc], s);
+      sV[V_CEFF + tid] = s;
+    }
+  }
 
   // GCN layers (state_encoder.py:194-197): h <- h + (sum_{nbr} he) / (deg + eps), pull over the CSR
   int exact_last = 0;
@@ -665,32 +1075,34 @@ __device__ void graph_body(const StepArgs& a, const BlobHeader& hd, const GraphD
     if (exact) pull_forward<true>(g, q, TRAIN && l == 0, g.H1g, l == 1, msum, hsum);
     else pull_forward<false>(g, q, TRAIN && l == 0, g.H1g, l == 1, msum, hsum);
     if (l == 1) {   // masked means (state_encoder.py:179-182,199-200); sum_j he_j = 1/2 sum_i acc_i
-      block_sum_q4(msum, sRed, sV + V_TMP16);
-      block_sum_q4(hsum, sRed, sV + V_TMP16B);
+      block_sum_q8(msum, hsum, sRed, sV + V_TMP32);
       if (tid < 16) {
-        sV[V_SV + 16 + tid] = sV[V_TMP16B + tid] / (float)n;
-        sV[V_SV + 32 + tid] = (0.5f * sV[V_TMP16 + tid]) / (float)e;
+        sV[V_SV + 32 + tid] = (0.5f * sV[V_TMP32 + tid]) / (float)e;
+        sV[V_SV + 16 + tid] = sV[V_TMP32 + 16 + tid] / (float)n;
       }
+    } else {
+      __syncthreads();
     }
-    __syncthreads();
     UPB_STAMP(4+l*2);
   }
 
-  // attention of the current node over all nodes (state_encoder.py:150-161)
-  if (tid < 16) {
-    float s = sW[S_QBC + tid];
-    for (int c = 0; c < 16; ++c) s = fmaf(sW[S_QC + tid * 16 + c], sV[V_HC + c], s);
-    sV[V_QP + tid] = s;
-  }
-  __syncthreads();
-  if (tid < 16) {
-    float s = 0.f;
-    for (int r = 0; r < 16; ++r) s = fmaf(sW[S_KC + r * 16 + tid], sV[V_QP + r], s);
-    sV[V_QK + tid] = 0.25f * s;     // 1/sqrt(head_dim)
-  }
-  __syncthreads();
+  // attention of the current node over all nodes (state_encoder.py:150-161).  q' and Kc^T q'/4 are small enough
+  // for every warp to compute for itself in registers (lane & 15 = component): no barriers, no smem round trip.
+  float qk_c;
   {
-    const float4 qk4 = ld4(sV + V_QK + q * 4);
+    const int c = lane & 15;
+    float qp = sW[S_QBC + c];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) qp = fmaf(sW[S_QCT + j * 16 + c], sV[V_HC + j], qp);        // q'[c] = Qc[c][:] . hc
+    float s = 0.f;
+#pragma unroll
+    for (int r = 0; r < 16; ++r) s = fmaf(sW[S_KC + r * 16 + c], __shfl_sync(0xffffffffu, qp, r), s);
+    qk_c = 0.25f * s;     // 1/sqrt(head_dim)
+    if (warp == 0 && lane < 16) { sV[V_QP + c] = qp; sV[V_QK + c] = qk_c; }
+  }
+  {
+    const float4 qk4 = make_float4(__shfl_sync(0xffffffffu, qk_c, q * 4), __shfl_sync(0xffffffffu, qk_c, q * 4 + 1),
+                                   __shfl_sync(0xffffffffu, qk_c, q * 4 + 2), __shfl_sync(0xffffffffu, qk_c, q * 4 + 3));
     float lmax = -CUDART_INF_F;
     for (int task = tid; task < ((n * 4 + 31) & ~31); task += NT) {
       const int i = task >> 2;
@@ -702,312 +1114,185 @@ __device__ void graph_body(const StepArgs& a, const BlobHeader& hd, const GraphD
         lmax = fmaxf(lmax, s);
       }
     }
-    const float smax = block_max1(lmax, sRed);   // barrier inside also publishes alpha
+    const float smax = block_max1(lmax, sRed);   // (alpha[i] is re-read below only by the warp that wrote it)
     float4 hb = f4(0.f);
     float asum = 0.f;
-    for (int task = tid; task < n * 4; task += NT) {
+    for (int task = tid; task < ((n * 4 + 31) & ~31); task += NT) {
       const int i = task >> 2;
-      const float ai = expf(g.alpha[i] - smax);
-      hb = hb + ld4(g.H + i * 16 + q * 4) * ai;
-      if (q == 0) asum += ai;
+      const float ai = i < n ? expf(g.alpha[i] - smax) : 0.f;
+      if (i < n) hb = hb + ld4(g.H + i * 16 + q * 4) * ai;
+      __syncwarp();                               // all four lanes of the node have read the score
+      if (i < n && q == 0) { g.alpha[i] = ai; asum += ai; }
     }
-    __syncthreads();                              // everyone has read alpha (scores) before it becomes weights
-    for (int i = tid; i < n; i += NT) g.alpha[i] = expf(g.alpha[i] - smax);
-    const float Z = block_sum1(asum, sRed);
-    block_sum_q4(hb, sRed, sV + V_TMP16);
-    if (tid < 16) sV[V_HBAR + tid] = sV[V_TMP16 + tid] / Z;
-    if (tid == 0) sc[SC_Z] = Z;
-    __syncthreads();
+    block_sum_q4p1(hb, asum, sRed, sV + V_TMP32);   // -> [0..15] sum a_i h_i, [16] sum a_i
   }
-  if (tid < 16) {
-    float s = sW[S_VBC + tid];
-    for (int c = 0; c < 16; ++c) s = fmaf(sW[S_VC + tid * 16 + c], sV[V_HBAR + c], s);
-    sV[V_VP + tid] = s;
-  }
-  __syncthreads();
-  if (tid < 16) {
-    float s = sW[S_BO + tid];
-    for (int c = 0; c < 16; ++c) s = fmaf(sW[S_WO + tid * 16 + c], sV[V_VP + c], s);
-    sV[V_SV + 48 + tid] = s;
-  }
-  if (tid < 3) sV[V_SV + 64 + tid] = (tid == g.stage) ? 1.f : 0.f;
-  __syncthreads();
   UPB_STAMP(7);
 
-  // value head (value.py:15-39)
-  matvec8<true>(P + P_VAL_W0, P + P_VAL_B0, HID, SVD, sV + V_SV, sV + V_Y0);
-  __syncthreads();
-  matvec8<true>(P + P_VAL_W1, P + P_VAL_B1, HID, HID, sV + V_Y0, sV + V_Y1);
-  __syncthreads();
-  UPB_STAMP(8);
-  if (warp == 0) {
-    const float v = warp_sum(__ldg(P + P_VAL_W2 + lane) * sV[V_Y1 + lane]) + __ldg(P + P_VAL_B2);
-    if (lane == 0) sc[SC_VALUE] = v;
-  }
-
-  // policy head on the mask-true candidates of the active stage (policy.py:45-65)
-  float wrow[16];
-  float cb, w2;
-  if (g.stage == 0) {
-    if (tid < 512) {   // Weff = Wa + Wd + Wc diag(hc), ceff = b + (Wb - Wd) hc   (state_encoder.py:207-210 folded in)
-      const int r = tid >> 4, c = tid & 15;
-      const float* w = sW + S_LUW0 + r * 64;
-      const float weff = w[c] + w[48 + c] + w[32 + c] * sV[V_HC + c];
-      sV[V_WEFFT + c * 32 + r] = weff;
-      sV[V_WEFF + r * 16 + c] = weff;
-      if (tid < 32) {
-        const float* wr = sW + S_LUW0 + tid * 64;
-        float s = sW[S_LUB0 + tid];
-        for (int cc = 0; cc < 16; ++cc) s = fmaf(wr[16 + cc] - wr[48 + cc], sV[V_HC + cc], s);
-        sV[V_CEFF + tid] = s;
-      }
+  // attention tail in every warp's registers; warp 0 publishes it
+  {
+    float hbar, vp, at;
+    attention_tail(sW, sV + V_TMP32, lane, hbar, vp, at);
+    if (warp == 0) {
+      if (lane < 16) { sV[V_HBAR + lane] = hbar; sV[V_VP + lane] = vp; sV[V_SV + 48 + lane] = at; }
+      if (lane < 3) sV[V_SV + 64 + lane] = (lane == g.stage) ? 1.f : 0.f;
+      if (lane == 0) sc[SC_Z] = sV[V_TMP32 + 16];
     }
-    __syncthreads();
-#pragma unroll
-    for (int c = 0; c < 16; ++c) wrow[c] = sV[V_WEFFT + c * 32 + lane];
-    cb = sV[V_CEFF + lane];
-    w2 = sW[S_LUW1 + lane];
-  } else {
-#pragma unroll
-    for (int c = 0; c < 16; ++c) wrow[c] = sW[S_RDW0T + c * 32 + lane];
-    cb = sW[S_RDB0 + lane];
-    w2 = sW[S_RDW1 + lane];
   }
-  for (int j = warp; j < k; j += NW) {
-    float t, xin;
-    head_unit(g, j, wrow, cb, t, xin);
-    const float zj = warp_sum(w2 * t);
-    if (lane == 0) g.z[j] = zj;
+  if (warp < 8) {
+    group_bar(1, 256);                             // sv published by warp 0
+    value_head_group(sV, vn, sc, tid);             // value head (value.py:15-39): warps 0..7
+  }
+  {   // policy head on the mask-true candidates (policy.py:45-65): half-warps pull candidates from a shared queue
+    HeadLane hl;
+    head_lane_init(hl, g, sW, sV, lane);
+    int* queue = reinterpret_cast<int*>(sc) + SC_QUEUE;
+    for (;;) {
+      int j = 0;
+      if ((lane & 15) == 0) j = atomicAdd(queue, 1);
+      j = __shfl_sync(hl.mask, j, 0, 16);
+      if (j >= k) break;
+      float t0, t1, xin;
+      head_units(hl, g, j, lane, t0, t1, xin);
+      const float zj = half_sum(hl.w20 * t0 + hl.w21 * t1, hl.mask);
+      if ((lane & 15) == 0) g.z[j] = zj;
+    }
   }
   __syncthreads();
   UPB_STAMP(9);
-  {   // masked softmax statistics: log-softmax over the candidates equals log-softmax over all padded logits
-    float lmax = -CUDART_INF_F;
-    int lbest = 0x7fffffff;
-    for (int j = tid; j < k; j += NT) {
-      const float zj = g.z[j];
-      if (zj > lmax) { lmax = zj; lbest = j; }
-    }
-    // block arg-max with first-index tie break (policy.py:72 `probs.argmax`)
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float om = __shfl_xor_sync(0xffffffffu, lmax, o);
-      const int ob = __shfl_xor_sync(0xffffffffu, lbest, o);
-      if (om > lmax || (om == lmax && ob < lbest)) { lmax = om; lbest = ob; }
-    }
-    if (lane == 0) { sRed[warp] = lmax; sRed[NW + warp] = __int_as_float(lbest); }
-    __syncthreads();
-    float zmax = sRed[0];
-    int best = __float_as_int(sRed[NW]);
-    for (int w = 1; w < NW; ++w) {
-      const float om = sRed[w];
-      const int ob = __float_as_int(sRed[NW + w]);
-      if (om > zmax || (om == zmax && ob < best)) { zmax = om; best = ob; }
-    }
-    __syncthreads();
-    float lsum = 0.f;
-    for (int j = tid; j < k; j += NT) lsum += expf(g.z[j] - zmax);
-    const float ssum = block_sum1(lsum, sRed);
-    const float lse = zmax + logf(ssum);
-    float lent = 0.f;
-    int aidx = -1;
-    if (a.actions) aidx = (int)a.actions[(size_t)gid * 2 + g.stage];
-    for (int j = tid; j < k; j += NT) {
-      const float lp = g.z[j] - lse;
-      lent -= expf(lp) * lp;
-      if (g.cidx[j] == aidx) sc[SC_SLOT] = (float)(j + 1);
-    }
-    const float ent = block_sum1(lent, sRed);    // barriers inside publish SC_SLOT
-    if (tid == 0) {
-      float logp = 0.f, H = ent;
-      int greedy = 0;
-      const int slot = (int)sc[SC_SLOT] - 1;
-      if (k > 0) {
-        greedy = g.cidx[best];
-        if (a.actions) logp = slot >= 0 ? g.z[slot] - lse : MASK_FILL - lse;
-      } else {      // every logit equals the fill value: uniform over the padded width
-        const float cap = (float)(g.stage == 0 ? hd.e_cap : hd.n_cap);
-        H = logf(cap);
-        if (a.actions) logp = -logf(cap);
-      }
-      sc[SC_LSE] = lse; sc[SC_ENT] = H; sc[SC_LOGP] = logp;
-      if (a.out_value) a.out_value[gid] = sc[SC_VALUE];
-      if (a.out_logp) a.out_logp[gid] = logp;
-      if (a.out_entropy) a.out_entropy[gid] = H;
-      if (a.out_greedy) a.out_greedy[gid] = greedy;
-    }
-    __syncthreads();
-    UPB_STAMP(10);
-  }
+  // softmax / outputs / PPO seeds by warp NW-1; meanwhile (TRAIN) warps 0..7 run the value-head and numeric-encoder
+  // backward, which only needs the value
+  if (warp == NW - 1) softmax_seeds<TRAIN>(a, hd, g, sc, gp, lane);
   if constexpr (!TRAIN) return;
+  if (warp < 8) {
+    const float gV = 2.f * a.c_value * (sc[SC_VALUE] - sc[SC_RET]) * a.inv_batch;
+    value_numeric_bwd_group(sV, vn, gV, gp, tid);
+  }
+  if (tid >= 256 && tid < 272) sV[V_GHC + tid - 256] = 0.f;
+  __syncthreads();
+  UPB_STAMP(10);
 
   // ================================================================================ backward
-  if (tid == 0) {
-    const float V = sc[SC_VALUE], R = a.ret[gid], logp = sc[SC_LOGP], H = sc[SC_ENT];
-    const float dv = V - R;
-    float glp = 0.f, gH = 0.f, surr = 0.f, negent = 0.f, in_ind = 0.f;
-    if (a.exps[gid] != 0.f) {
-      in_ind = 1.f;
-      const float r = expf(logp - a.fixed_lp[gid]), A = a.adv[gid];
-      const float lo = 1.f - a.clip_eps, hi = 1.f + a.clip_eps;
-      const float s1 = r * A, s2 = fminf(fmaxf(r, lo), hi) * A;
-      surr = -fminf(s1, s2);
-      if ((r >= lo && r <= hi) || s1 < s2) glp = -A * r * a.inv_ind;
-      gH = -a.c_entropy * a.inv_ind;
-      negent = -H;
-    }
-    sc[SC_GV] = 2.f * a.c_value * dv * a.inv_batch;
-    sc[SC_GLP] = glp;
-    sc[SC_GH] = gH;
-    float* st = gp + G_STATS;
-    st[0] += dv * dv; st[1] += surr; st[2] += negent; st[3] += 1.f; st[4] += in_ind;
-    st[5] += g.stage == 0 ? 1.f : 0.f; st[6] += g.stage == 1 ? 1.f : 0.f;
-    st[7] += (isfinite(V) && isfinite(logp) && isfinite(H)) ? 0.f : 1.f;
-  }
-  __syncthreads();
-  {   // logits gradient: g_z = g_lp (delta_a - p) - g_H p (logp + H)
-    const float glp = sc[SC_GLP], gH = sc[SC_GH], lse = sc[SC_LSE], H = sc[SC_ENT];
-    const int slot = (int)sc[SC_SLOT] - 1;
-    for (int j = tid; j < k; j += NT) {
-      const float lp = g.z[j] - lse, p = expf(lp);
-      g.gz[j] = glp * ((j == slot ? 1.f : 0.f) - p) - gH * p * (lp + H);
-    }
-  }
-  if (tid < 16) sV[V_GHC + tid] = 0.f;
-  __syncthreads();
-  UPB_STAMP(11);
-
-  // ---- policy head backward, CH candidates at a time (chunk buffers alias the GPQ region / shared scratch)
+  // ---- policy head backward, CH candidates at a time
   {
-    float* cGU = smem + S_GPQ;              // [CH][32] g_u
-    float* cGT = cGU + CH * 32;             // [CH][32] g_z * t
-    float* cX = cGT + CH * 32;              // [CH][16] head input
-    float G = 0.f, gcr = 0.f, gw2r = 0.f;   // thread (r = tid>>4, c = tid&15)
-    const int r_ = tid >> 4, c_ = tid & 15;
-    const float* WR = g.stage == 0 ? sV + V_WEFF : sW + S_RDW0;     // [32][16] row-major (conflict-free below)
-    for (int base = 0; base < k; base += CH) {
+    float* cGU = smem + S_GPQ + HB_GU;        // [CH][32] g_u
+    float* cX = smem + S_GPQ + HB_X;          // [CH][16] head input
+    float* pGC = smem + S_GPQ + HB_PGC;       // [32][32] per-half-warp partial sums of g_u
+    float* pGW2 = smem + S_GPQ + HB_PGW2;     // [32][32] per-half-warp partial sums of g_z t
+    float G = 0.f, gcr = 0.f, gw2r = 0.f;     // thread (r = tid>>4, c = tid&15)
+    const int r_ = (tid >> 4) & 31, c_ = tid & 15;
+    const float* WR = g.stage == 0 ? sV + V_WEFF : sW + S_RDW0;     // [32][16] row-major
+    int base = 0;
+    do {
       const int cn = min(CH, k - base);
-      for (int jj = warp; jj < cn; jj += NW) {
-        float t, xin;
-        head_unit(g, base + jj, wrow, cb, t, xin);
-        const float gzj = g.gz[base + jj];
-        cGU[jj * 32 + lane] = gzj * w2 * (1.f - t * t);
-        cGT[jj * 32 + lane] = gzj * t;
-        if (lane < 16) cX[jj * 16 + lane] = xin;
+      {
+        HeadLane hl;
+        head_lane_init(hl, g, sW, sV, lane);
+        const int hw = warp * 2 + (lane >> 4);
+        float a00 = 0.f, a01 = 0.f, a10 = 0.f, a11 = 0.f;
+        for (int jj = hw; jj < cn; jj += 2 * NW) {
+          float t0, t1, xin;
+          head_units(hl, g, base + jj, lane, t0, t1, xin);
+          const float gzj = g.gz[base + jj];
+          const float gu0 = gzj * hl.w20 * (1.f - t0 * t0), gu1 = gzj * hl.w21 * (1.f - t1 * t1);
+          cGU[jj * 32 + (lane & 15)] = gu0;
+          cGU[jj * 32 + (lane & 15) + 16] = gu1;
+          cX[jj * 16 + (lane & 15)] = xin;
+          a00 += gu0; a01 += gu1; a10 = fmaf(gzj, t0, a10); a11 = fmaf(gzj, t1, a11);
+        }
+        pGC[hw * 32 + (lane & 15)] = a00; pGC[hw * 32 + (lane & 15) + 16] = a01;
+        pGW2[hw * 32 + (lane & 15)] = a10; pGW2[hw * 32 + (lane & 15) + 16] = a11;
       }
       __syncthreads();
+      UPB_STAMP(12);
       if (tid < 512) {
-        for (int jj = 0; jj < cn; ++jj) {
-          const float gu = cGU[jj * 32 + r_];
-          G = fmaf(gu, cX[jj * 16 + c_], G);
-          if (c_ == 0) { gcr += gu; gw2r += cGT[jj * 32 + r_]; }
+        float g0 = 0.f, g1 = 0.f;
+        int jj = 0;
+        for (; jj + 1 < cn; jj += 2) {
+          g0 = fmaf(cGU[jj * 32 + r_], cX[jj * 16 + c_], g0);
+          g1 = fmaf(cGU[(jj + 1) * 32 + r_], cX[(jj + 1) * 16 + c_], g1);
+        }
+        if (jj < cn) g0 = fmaf(cGU[jj * 32 + r_], cX[jj * 16 + c_], g0);
+        G += g0 + g1;
+        if (tid < 64) {       // sums over the 32 half-warps: tid < 32 -> g_c[tid], 32..63 -> g_w2[tid-32]
+          const float* src = tid < 32 ? pGC + tid : pGW2 + (tid - 32);
+          float sacc = 0.f;
+#pragma unroll 8
+          for (int h = 0; h < 32; ++h) sacc += src[h * 32];
+          if (tid < 32) gcr += sacc; else gw2r += sacc;
         }
       }
       for (int task = tid; task < cn * 16; task += NT) {   // g_x = W^T g_u
         const int jj = task >> 4, c = task & 15;
-        float s = 0.f;
+        float s0 = 0.f, s1 = 0.f;
 #pragma unroll 8
-        for (int r = 0; r < 32; ++r) s = fmaf(WR[r * 16 + c], cGU[jj * 32 + r], s);
-        g.ghead[(size_t)(base + jj) * 16 + c] = s;
-      }
-      __syncthreads();
-    }
-    if (tid < 512) {
-      sV[V_GWEFF + tid] = G;
-      if (c_ == 0) { sV[V_GC + r_] = gcr; sV[V_GW2 + r_] = gw2r; }
-    }
-    __syncthreads();
-    UPB_STAMP(12);
-    if (g.stage == 0) {
-      if (tid < 512) {
-        const float hc = sV[V_HC + c_], gc = sV[V_GC + r_];
-        const int o = P_LU_W0 + r_ * 64 + c_;
-        gacc(gp, o, G);
-        gacc(gp, o + 16, gc * hc);
-        gacc(gp, o + 32, G * hc);
-        gacc(gp, o + 48, G - gc * hc);
-      }
-      if (tid < 32) { gacc(gp, P_LU_B0 + tid, sV[V_GC + tid]); gacc(gp, P_LU_W1 + tid, sV[V_GW2 + tid]); }
-      if (tid < 16) {   // d/d hc through ceff and through Wc diag(hc)
-        float s = 0.f;
-        for (int r = 0; r < 32; ++r) {
-          const float* w = sW + S_LUW0 + r * 64;
-          s = fmaf(w[16 + tid] - w[48 + tid], sV[V_GC + r], s);
-          s = fmaf(w[32 + tid], sV[V_GWEFF + r * 16 + tid], s);
+        for (int r = 0; r < 32; r += 2) {
+          s0 = fmaf(WR[r * 16 + c], cGU[jj * 32 + r], s0);
+          s1 = fmaf(WR[(r + 1) * 16 + c], cGU[jj * 32 + r + 1], s1);
         }
-        sV[V_GHC + tid] = s;
+        g.ghead[(size_t)(base + jj) * 16 + c] = s0 + s1;
       }
-    } else {
-      if (tid < 512) gacc(gp, P_RD_W0 + tid, G);
-      if (tid < 32) { gacc(gp, P_RD_B0 + tid, sV[V_GC + tid]); gacc(gp, P_RD_W1 + tid, sV[V_GW2 + tid]); }
+      base += CH;
+      if (base < k) __syncthreads();               // chunk buffers are reused
+    } while (base < k);
+    if (tid < 512) sV[V_GWEFF + tid] = G;
+    if (tid < 32) sV[V_GC + tid] = gcr;
+    if (tid >= 32 && tid < 64) sV[V_GW2 + tid - 32] = gw2r;
+  }
+  __syncthreads();
+  if (g.stage == 0) {
+    if (tid < 512) {
+      const int r_ = tid >> 4, c_ = tid & 15;
+      const float G = sV[V_GWEFF + tid], hc = sV[V_HC + c_], gc = sV[V_GC + r_];
+      const int o = P_LU_W0 + r_ * 64 + c_;
+      gacc(gp, o, G);
+      gacc(gp, o + 16, gc * hc);
+      gacc(gp, o + 32, G * hc);
+      gacc(gp, o + 48, G - gc * hc);
+    }
+    if (tid < 32) { gacc(gp, P_LU_B0 + tid, sV[V_GC + tid]); gacc(gp, P_LU_W1 + tid, sV[V_GW2 + tid]); }
+    if (warp == 1 && lane < 16) {   // d/d hc through ceff and through Wc diag(hc)
+      float s = 0.f;
+#pragma unroll 8
+      for (int r = 0; r < 32; ++r) {
+        const float* w = sW + S_LUW0 + r * 64;
+        s = fmaf(w[16 + lane] - w[48 + lane], sV[V_GC + r], s);
+        s = fmaf(w[32 + lane], sV[V_GWEFF + r * 16 + lane], s);
+      }
+      sV[V_GHC + lane] = s;
+    }
+  } else {
+    if (tid < 512) gacc(gp, P_RD_W0 + tid, sV[V_GWEFF + tid]);
+    if (tid < 32) { gacc(gp, P_RD_B0 + tid, sV[V_GC + tid]); gacc(gp, P_RD_W1 + tid, sV[V_GW2 + tid]); }
+  }
+
+  // ---- attention backward.  g_v' = Wo^T g_att and g_hbar = Vc^T g_v' per warp in registers (lane & 15 = component).
+  float gvp_c, ghbar_c;
+  {
+    const int c = lane & 15;
+    const float gatt = sV[V_GSV + 48 + c];
+    float s = 0.f;
+#pragma unroll
+    for (int r = 0; r < 16; ++r) s = fmaf(sW[S_WO + r * 16 + c], __shfl_sync(0xffffffffu, gatt, r), s);
+    gvp_c = s;
+    s = 0.f;
+#pragma unroll
+    for (int r = 0; r < 16; ++r) s = fmaf(sW[S_VC + r * 16 + c], __shfl_sync(0xffffffffu, gvp_c, r), s);
+    ghbar_c = s;
+    if (warp == 0 && lane < 16) {
+      sV[V_GVP + c] = gvp_c;
+      sV[V_CE + c] = e > 0 ? sV[V_GSV + 32 + c] / (float)e : 0.f;
     }
   }
-
-  // ---- value head backward (value.py:36-39)
-  if (tid < 32) sV[V_D1 + tid] = sc[SC_GV] * __ldg(P + P_VAL_W2 + tid) * (1.f - sV[V_Y1 + tid] * sV[V_Y1 + tid]);
-  __syncthreads();
-  if (tid < 32) {
-    float s = 0.f;
-#pragma unroll
-    for (int r = 0; r < 32; ++r) s = fmaf(__ldg(P + P_VAL_W1 + r * 32 + tid), sV[V_D1 + r], s);
-    sV[V_D0 + tid] = s * (1.f - sV[V_Y0 + tid] * sV[V_Y0 + tid]);
-  }
-  __syncthreads();
-  if (tid < SVD) {
-    float s = 0.f;
-#pragma unroll
-    for (int r = 0; r < 32; ++r) s = fmaf(__ldg(P + P_VAL_W0 + r * SVD + tid), sV[V_D0 + r], s);
-    sV[V_GSV + tid] = s;
-  }
-  for (int idx = tid; idx < HID * SVD; idx += NT) gacc(gp, P_VAL_W0 + idx, sV[V_D0 + idx / SVD] * sV[V_SV + idx % SVD]);
-  for (int idx = tid; idx < HID * HID; idx += NT) gacc(gp, P_VAL_W1 + idx, sV[V_D1 + (idx >> 5)] * sV[V_Y0 + (idx & 31)]);
-  if (tid < 32) {
-    gacc(gp, P_VAL_B0 + tid, sV[V_D0 + tid]);
-    gacc(gp, P_VAL_B1 + tid, sV[V_D1 + tid]);
-    gacc(gp, P_VAL_W2 + tid, sc[SC_GV] * sV[V_Y1 + tid]);
-  }
-  if (tid == 32) gacc(gp, P_VAL_B2, sc[SC_GV]);
-  __syncthreads();
-  // ---- numeric encoder backward
-  if (tid < 16) sV[V_DN1 + tid] = sV[V_GSV + tid] * (1.f - sV[V_SV + tid] * sV[V_SV + tid]);
-  __syncthreads();
-  if (tid < NH0) {
-    float s = 0.f;
-#pragma unroll
-    for (int r = 0; r < 16; ++r) s = fmaf(__ldg(P + P_NUM_W1 + r * NH0 + tid), sV[V_DN1 + r], s);
-    sV[V_DN0 + tid] = s * (1.f - sV[V_A0 + tid] * sV[V_A0 + tid]);
-  }
-  __syncthreads();
-  UPB_STAMP(13);
-  for (int idx = tid; idx < 16 * NH0; idx += NT) gacc(gp, P_NUM_W1 + idx, sV[V_DN1 + (idx >> 6)] * sV[V_A0 + (idx & 63)]);
-  for (int idx = tid; idx < NH0 * NUMD; idx += NT) gacc(gp, P_NUM_W0 + idx, sV[V_DN0 + idx / NUMD] * sV[V_X52 + idx % NUMD]);
-  if (tid < 16) gacc(gp, P_NUM_B1 + tid, sV[V_DN1 + tid]);
-  if (tid < NH0) gacc(gp, P_NUM_B0 + tid, sV[V_DN0 + tid]);
-
-  // ---- attention backward
-  if (tid < 16) {   // g_v' = Wo^T g_att
-    float s = 0.f;
-    for (int r = 0; r < 16; ++r) s = fmaf(sW[S_WO + r * 16 + tid], sV[V_GSV + 48 + r], s);
-    sV[V_GVP + tid] = s;
-    sV[V_GMN + tid] = sV[V_GSV + 16 + tid] / (float)n;
-    sV[V_CE + tid] = e > 0 ? sV[V_GSV + 32 + tid] / (float)e : 0.f;
-  }
-  __syncthreads();
-  if (tid < 16) {   // g_hbar = Vc^T g_v'
-    float s = 0.f;
-    for (int r = 0; r < 16; ++r) s = fmaf(sW[S_VC + r * 16 + tid], sV[V_GVP + r], s);
-    sV[V_GHBAR + tid] = s;
-  }
-  __syncthreads();
-  if (tid == 0) {
-    float s = 0.f;
-    for (int c = 0; c < 16; ++c) s = fmaf(sV[V_GHBAR + c], sV[V_HBAR + c], s);
-    sc[SC_GDOT] = s;
-  }
-  __syncthreads();
   {
-    const float4 gh4 = ld4(sV + V_GHBAR + q * 4), qk4 = ld4(sV + V_QK + q * 4), gmn4 = ld4(sV + V_GMN + q * 4);
-    const float invZ = 1.f / sc[SC_Z], gdot = sc[SC_GDOT];
+    float gdot = ghbar_c * sV[V_HBAR + (lane & 15)];
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) gdot += __shfl_xor_sync(0xffffffffu, gdot, o);     // sum over the 16 components
+    const float4 gh4 = make_float4(__shfl_sync(0xffffffffu, ghbar_c, q * 4), __shfl_sync(0xffffffffu, ghbar_c, q * 4 + 1),
+                                   __shfl_sync(0xffffffffu, ghbar_c, q * 4 + 2), __shfl_sync(0xffffffffu, ghbar_c, q * 4 + 3));
+    const float4 qk4 = make_float4(__shfl_sync(0xffffffffu, qk_c, q * 4), __shfl_sync(0xffffffffu, qk_c, q * 4 + 1),
+                                   __shfl_sync(0xffffffffu, qk_c, q * 4 + 2), __shfl_sync(0xffffffffu, qk_c, q * 4 + 3));
+    const float4 gmn4 = ld4(sV + V_GSV + 16 + q * 4) * (1.f / (float)n);
+    const float invZ = 1.f / sc[SC_Z];
     float4 gsh = f4(0.f);
     for (int task = tid; task < ((n * 4 + 31) & ~31); task += NT) {
       const int i = task >> 2;
@@ -1019,34 +1304,35 @@ __device__ void graph_body(const StepArgs& a, const BlobHeader& hd, const GraphD
         const float ai = g.alpha[i] * invZ;
         const float gs = ai * (dp - gdot);
         gsh = gsh + h * gs;
-        // g_h^L = g_mean/n + a_i g_hbar (value path) + g_s qk (key path); in place over h^L
-        st4(g.H + i * 16 + q * 4, (gmn4 + gh4 * ai + qk4 * gs) * g.inv[i]);   // stored scaled by 1/(deg+eps)
+        // g_h^L = g_mean/n + a_i g_hbar (value path) + g_s qk (key path); stored scaled by 1/(deg+eps), over h^L
+        st4(g.H + i * 16 + q * 4, (gmn4 + gh4 * ai + qk4 * gs) * g.inv[i]);
       }
     }
     block_sum_q4(gsh, sRed, sV + V_GSH);
   }
-  if (tid < 16) {   // g_q' = Kc gsh / 4
+  if (warp == 0) {   // g_q' = Kc gsh / 4, g_hc += Qc^T g_q', composed-projection gradients
+    const int c = lane & 15;
     float s = 0.f;
-    for (int c = 0; c < 16; ++c) s = fmaf(sW[S_KC + tid * 16 + c], sV[V_GSH + c], s);
-    sV[V_GQP + tid] = 0.25f * s;
-  }
-  __syncthreads();
-  if (tid < 16) {   // g_hc += Qc^T g_q'
-    float s = sV[V_GHC + tid];
-    for (int r = 0; r < 16; ++r) s = fmaf(sW[S_QC + r * 16 + tid], sV[V_GQP + r], s);
-    sV[V_GHC + tid] = s;
-  }
-  if (tid < 256) {
-    const int r = tid >> 4, c = tid & 15;
-    gacc(gp, G_QC + tid, sV[V_GQP + r] * sV[V_HC + c]);
-    gacc(gp, G_KC + tid, 0.25f * sV[V_QP + r] * sV[V_GSH + c]);
-    gacc(gp, G_VC + tid, sV[V_GVP + r] * sV[V_HBAR + c]);
-    gacc(gp, P_MHA_OUT_W + tid, sV[V_GSV + 48 + r] * sV[V_VP + c]);
-  }
-  if (tid < 16) {
-    gacc(gp, G_QBC + tid, sV[V_GQP + tid]);
-    gacc(gp, G_VBC + tid, sV[V_GVP + tid]);
-    gacc(gp, P_MHA_OUT_B + tid, sV[V_GSV + 48 + tid]);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) s = fmaf(sW[S_KCT + j * 16 + c], sV[V_GSH + j], s);
+    const float gqp = 0.25f * s;
+    float t = sV[V_GHC + c];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) t = fmaf(sW[S_QC + r * 16 + c], __shfl_sync(0xffffffffu, gqp, r), t);
+    if (lane < 16) { sV[V_GHC + c] = t; sV[V_GQP + c] = gqp; }
+    __syncwarp();
+    for (int idx = lane; idx < 256; idx += 32) {
+      const int r = idx >> 4, cc = idx & 15;
+      gacc(gp, G_QC + idx, sV[V_GQP + r] * sV[V_HC + cc]);
+      gacc(gp, G_KC + idx, 0.25f * sV[V_QP + r] * sV[V_GSH + cc]);
+      gacc(gp, G_VC + idx, sV[V_GVP + r] * sV[V_HBAR + cc]);
+      gacc(gp, P_MHA_OUT_W + idx, sV[V_GSV + 48 + r] * sV[V_VP + cc]);
+    }
+    if (lane < 16) {
+      gacc(gp, G_QBC + lane, sV[V_GQP + lane]);
+      gacc(gp, G_VBC + lane, sV[V_GVP + lane]);
+      gacc(gp, P_MHA_OUT_B + lane, sV[V_GSV + 48 + lane]);
+    }
   }
   if (g.stage == 1) {   // road head feeds h^L of its candidate nodes directly
     for (int task = tid; task < k * 16; task += NT) {
@@ -1225,6 +1511,21 @@ __global__ void __launch_bounds__(NT, 1) k_sgnn(const __grid_constant__ StepArgs
         if (a.out_entropy) a.out_entropy[gid] = CUDART_NAN_F;
       }
       continue;
+    }
+    {   // pull the NEXT graph of this CTA into L2 while this one is processed (its first touches are then L2 hits)
+      const int nitem = item + gridDim.x;
+      if (nitem < a.count) {
+        const GraphDesc& nd = descs[a.ids ? a.ids[nitem] : nitem];
+        const char* px = reinterpret_cast<const char*>(a.blob + hd.off_x) + (size_t)nd.x_row * FS * 4;
+        const char* pa = reinterpret_cast<const char*>(a.blob + hd.off_adj) + (size_t)nd.adj_off * 4;
+        const char* pr = reinterpret_cast<const char*>(a.blob + hd.off_rowptr) + (size_t)nd.rp_off * 2;
+        const char* po = reinterpret_cast<const char*>(a.blob + hd.off_order) + (size_t)nd.ord_off * 2;
+        const int bx = nd.n * FS * 4, ba = nd.e * 8, br = (nd.n + 1) * 2, bo = nd.ord_rounds * NW * 16;
+        for (int o = threadIdx.x * 128; o < bx; o += NT * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(px + o));
+        for (int o = threadIdx.x * 128; o < ba; o += NT * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pa + o));
+        for (int o = threadIdx.x * 128; o < br; o += NT * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pr + o));
+        for (int o = threadIdx.x * 128; o < bo; o += NT * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(po + o));
+      }
     }
     const bool big = d.n > NS || 2 * d.e > AS || d.k > KS || d.ord_rounds > ORD_ROUNDS;
     if (big) graph_body<TRAIN, true>(a, hd, d, gid, smem, gp, scr, item == (int)blockIdx.x);
