@@ -29,6 +29,16 @@ BATCH = 256
 SEED = 111
 
 
+def read_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of one k_sgnn<TRAIN> launch from the committed `ncu --set full`
+    capture of this workload (profiles/traffic.json; cannot be measured inside a timed run)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return float(json.load(f)["k_sgnn_train_dram_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 def read_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -113,6 +123,18 @@ def cpu_port_step_time(states, actions, flat, steps: int, warmup: int, threads: 
     return float(np.mean(times))
 
 
+def best_cpu_threads(states, actions, flat, cores: int):
+    """The reference prescribes OMP_NUM_THREADS=1 (README.md:22-25) but the update path is faster with more threads;
+    SURVEY 8(d): time several settings and use the fastest as "reference CPU".  Probe on 32 graphs."""
+    cands = sorted({1, min(cores, 8), min(cores, 16), min(cores, 32), min(cores, 64), cores})
+    best, best_t = cands[0], float("inf")
+    for th in cands:
+        t = cpu_port_step_time(states[:32], actions[:32], flat, 1, 1, th)
+        if t < best_t:
+            best, best_t = th, t
+    return best, best_t / 32
+
+
 def run_reference(args):
     """--impl reference: the reference's own CPU PyTorch dataflow (oracle port; /root/reference is absent on the
     GPU box and cannot travel) on the host cores, same metric / config."""
@@ -124,11 +146,10 @@ def run_reference(args):
     states, actions = make_pool(SEED, args.community, min(args.distinct, BATCH), 1)
     flat = PL.default_init(SEED)
     # bounded sample: shrink the per-step sample so the whole run ends within a few minutes
-    probe = cpu_port_step_time(states[:32], actions[:32], flat, 1, 1, cores)
-    per_graph = probe / 32
+    threads, per_graph = best_cpu_threads(states, actions, flat, cores)
     budget = 150.0
     sample = int(max(16, min(BATCH, budget / max(per_graph * (args.steps + args.warmup), 1e-9))))
-    t = cpu_port_step_time(states[:sample], actions[:sample], flat, args.steps, args.warmup, cores)
+    t = cpu_port_step_time(states[:sample], actions[:sample], flat, args.steps, args.warmup, threads)
     value = sample / t
     out = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
@@ -136,8 +157,9 @@ def run_reference(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.community} PPO minibatch update, padded eager PyTorch on CPU (oracle port of the "
                                f"reference dataflow), {sample} graphs per step", "global_batch": sample},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{args.steps} steps x {sample} {args.community} graphs, torch threads={cores}"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "host_cores": cores,
+                         "sample": f"{args.steps} steps x {sample} {args.community} graphs, torch threads={threads} "
+                                   f"(fastest of 1/8/16/32/64/{cores})"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -237,6 +259,11 @@ def main():
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     total_ms = float(ms.item())
     launches = eng.launches - launches0
+    # the timed region lasts a few ms, too short for nvidia-smi: keep the same load for ~1 s more (same count on every
+    # rank) so the clock / throttle record describes this workload
+    for i in range(int(min(20000, max(0.0, 1000.0 / max(total_ms / args.steps, 1e-3))))):
+        step(args.warmup + i)
+    torch.cuda.synchronize()
     clk = clocks.stop() if rank == 0 else None
     value = BATCH * world * args.steps / (total_ms * 1e-3)
     losses = eng.read_losses(grad)
@@ -300,10 +327,11 @@ def main():
     if rank == 0 and world == 1 and not args.skip_cpu:
         cores = os.cpu_count() or 1
         sample = BATCH
-        tstep = cpu_port_step_time(states[:sample], actions[:sample], flat, 3, 1, cores)
-        cpu = {"value": sample / tstep, "unit": UNIT, "cores": cores, "kind": "port",
+        threads, _ = best_cpu_threads(states, actions, flat, cores)
+        tstep = cpu_port_step_time(states[:sample], actions[:sample], flat, 3, 1, threads)
+        cpu = {"value": sample / tstep, "unit": UNIT, "cores": threads, "kind": "port", "host_cores": cores,
                "sample": f"3 steps (after 1 warm-up) x {sample} {args.community} graphs padded to "
-                         f"{blob.n_cap}/{blob.e_cap}, torch threads={cores}"}
+                         f"{blob.n_cap}/{blob.e_cap}, torch threads={threads} (fastest of 1/8/16/32/64/{cores})"}
 
     if rank == 0:
         out = {
@@ -315,7 +343,7 @@ def main():
                        "global_batch": BATCH * world, "parallelism": f"dp{world}",
                        "l2_policy": f"inputs larger than L2: {args.pool} resident minibatches = {blob.nbytes / 1e6:.0f} MB cycled"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "k_sgnn<TRAIN>", "kernel_ms": k_avg_ms,
+                         "traffic": read_traffic(), "kernel": "k_sgnn<TRAIN>", "kernel_ms": k_avg_ms,
                          "algorithmic_bytes_per_launch": balg, "peak_source": peak_src,
                          "kernel_share_of_step": k_avg_ms / (total_ms / args.steps)},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
