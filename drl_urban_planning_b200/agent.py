@@ -49,7 +49,7 @@ def _default_engine(dev):
 class B200Update:
     """Owns the PPOUpdater of one agent and mirrors the weights between it and the agent's torch modules."""
 
-    def __init__(self, agent, clip_mode: int = _lib.CLIP_REFERENCE, process_group=None, device=None):
+    def __init__(self, agent, clip_mode: int = _lib.CLIP_REFERENCE, process_group="auto", device=None):
         cfg = agent.cfg
         self.agent = agent
         dev = torch.device(device) if device is not None else agent.device

@@ -32,7 +32,7 @@ class PPOUpdater:
     def __init__(self, flat_params, n_cap: int, e_cap: int, device, lr: float = 4e-4, eps: float = 1e-5,
                  clip_epsilon: float = 0.2, value_pred_coef: float = 0.5, entropy_coef: float = 0.01,
                  gamma: float = 1.0, tau: float = 0.0, opt_num_epochs: int = 4, mini_batch_size: int = 256,
-                 clip_mode: int = _lib.CLIP_REFERENCE, process_group=None, pack_threads: int = 0):
+                 clip_mode: int = _lib.CLIP_REFERENCE, process_group="auto", pack_threads: int = 0):
         self.device = torch.device(device)
         self.engine = Engine(self.device, n_cap, e_cap, lr=lr, eps=eps, clip_epsilon=clip_epsilon,
                              value_pred_coef=value_pred_coef, entropy_coef=entropy_coef, clip_mode=clip_mode)
@@ -46,9 +46,16 @@ class PPOUpdater:
         self.opt_num_epochs, self.mini_batch_size = opt_num_epochs, mini_batch_size
         self.value_pred_coef, self.entropy_coef = value_pred_coef, entropy_coef
         self.pack_threads = pack_threads
-        self.pg = process_group
+        # process_group: "auto" = the default group if torch.distributed is initialised, None = single process,
+        # or an explicit group
         self.world, self.rank = 1, 0
-        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+        if process_group == "auto":
+            process_group = None
+            use_dist = torch.distributed.is_available() and torch.distributed.is_initialized()
+        else:
+            use_dist = process_group is not None
+        self.pg = process_group
+        if use_dist:
             import torch.distributed as dist
             self.world = dist.get_world_size(process_group)
             self.rank = dist.get_rank(process_group)
