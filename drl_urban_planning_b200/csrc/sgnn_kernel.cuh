@@ -630,23 +630,47 @@ __device__ __forceinline__ void gacc(float* gp, int idx, float v) {
 // ---- small dense blocks run by single warps from shared-memory weights ------------------------------------------
 // value-head and numeric-encoder weights -> the (currently free) GPQ region, with padded row strides
 __device__ __forceinline__ void stage_vn_weights(const float* __restrict__ P, float* vn) {
+  // all global loads are issued before the first shared store, so the thread waits for one L2 round trip, not 18
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  for (int i = t; i < HID * SVD; i += NT) vn[VN_VW0 + i] = __ldg(P + P_VAL_W0 + i);       // same [32][67] layout
-  for (int i = t; i < HID * HID; i += NT) vn[VN_VW1 + (i >> 5) * 33 + (i & 31)] = __ldg(P + P_VAL_W1 + i);
-  for (int u = warp; u < NH0; u += NW) {                                                  // [64][52] -> row stride 53
-    vn[VN_NW0 + u * 53 + lane] = __ldg(P + P_NUM_W0 + u * NUMD + lane);
-    if (lane < NUMD - 32) vn[VN_NW0 + u * 53 + 32 + lane] = __ldg(P + P_NUM_W0 + u * NUMD + 32 + lane);
+  float a[5], b[2], c[8], d[2], e = 0.f;
+#pragma unroll
+  for (int j = 0; j < 5; ++j) a[j] = (t + NT * j < HID * SVD) ? __ldg(P + P_VAL_W0 + t + NT * j) : 0.f;
+#pragma unroll
+  for (int j = 0; j < 2; ++j) b[j] = __ldg(P + P_VAL_W1 + t + NT * j);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int u = warp + NW * j;
+    c[2 * j] = __ldg(P + P_NUM_W0 + u * NUMD + lane);
+    c[2 * j + 1] = lane < NUMD - 32 ? __ldg(P + P_NUM_W0 + u * NUMD + 32 + lane) : 0.f;
   }
-  for (int i = t; i < 16 * NH0; i += NT) vn[VN_NW1 + (i >> 6) * 65 + (i & 63)] = __ldg(P + P_NUM_W1 + i);
-  if (t < 32) {
-    vn[VN_VB0 + t] = __ldg(P + P_VAL_B0 + t);
-    vn[VN_VB1 + t] = __ldg(P + P_VAL_B1 + t);
-    vn[VN_VW2 + t] = __ldg(P + P_VAL_W2 + t);
+#pragma unroll
+  for (int j = 0; j < 2; ++j) d[j] = __ldg(P + P_NUM_W1 + t + NT * j);
+  if (t < 32) e = __ldg(P + P_VAL_B0 + t);
+  else if (t < 64) e = __ldg(P + P_VAL_B1 + t - 32);
+  else if (t < 96) e = __ldg(P + P_VAL_W2 + t - 64);
+  else if (t < 160) e = __ldg(P + P_NUM_B0 + t - 96);
+  else if (t < 176) e = __ldg(P + P_NUM_B1 + t - 160);
+  else if (t == 176) e = __ldg(P + P_VAL_B2);
+#pragma unroll
+  for (int j = 0; j < 5; ++j) if (t + NT * j < HID * SVD) vn[VN_VW0 + t + NT * j] = a[j];       // same [32][67] layout
+#pragma unroll
+  for (int j = 0; j < 2; ++j) { const int i = t + NT * j; vn[VN_VW1 + (i >> 5) * 33 + (i & 31)] = b[j]; }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {                                                                  // [64][52] -> stride 53
+    const int u = warp + NW * j;
+    vn[VN_NW0 + u * 53 + lane] = c[2 * j];
+    if (lane < NUMD - 32) vn[VN_NW0 + u * 53 + 32 + lane] = c[2 * j + 1];
   }
-  if (t >= 32 && t < 96) vn[VN_NB0 + t - 32] = __ldg(P + P_NUM_B0 + t - 32);
-  if (t >= 96 && t < 112) vn[VN_NB1 + t - 96] = __ldg(P + P_NUM_B1 + t - 96);
-  if (t == 112) vn[VN_VB2] = __ldg(P + P_VAL_B2);
+#pragma unroll
+  for (int j = 0; j < 2; ++j) { const int i = t + NT * j; vn[VN_NW1 + (i >> 6) * 65 + (i & 63)] = d[j]; }
+  if (t < 32) vn[VN_VB0 + t] = e;
+  else if (t < 64) vn[VN_VB1 + t - 32] = e;
+  else if (t < 96) vn[VN_VW2 + t - 64] = e;
+  else if (t < 160) vn[VN_NB0 + t - 96] = e;
+  else if (t < 176) vn[VN_NB1 + t - 160] = e;
+  else if (t == 176) vn[VN_VB2] = e;
 }
+static_assert(NT == 512 && NW == 16, "stage_vn_weights is laid out for 512 threads");
 
 __device__ __forceinline__ void group_bar(int id, int nthreads) {      // named barrier of a warp group
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -1250,15 +1274,18 @@ __device__ void graph_body(const StepArgs& a, const BlobHeader& hd, const GraphD
       gacc(gp, o + 48, G - gc * hc);
     }
     if (tid < 32) { gacc(gp, P_LU_B0 + tid, sV[V_GC + tid]); gacc(gp, P_LU_W1 + tid, sV[V_GW2 + tid]); }
-    if (warp == 1 && lane < 16) {   // d/d hc through ceff and through Wc diag(hc)
-      float s = 0.f;
-#pragma unroll 8
-      for (int r = 0; r < 32; ++r) {
-        const float* w = sW + S_LUW0 + r * 64;
-        s = fmaf(w[16 + lane] - w[48 + lane], sV[V_GC + r], s);
-        s = fmaf(w[32 + lane], sV[V_GWEFF + r * 16 + lane], s);
+    if (warp == 1) {   // d/d hc through ceff and through Wc diag(hc): 16 components x 2 halves of the 32 units
+      const int c = lane & 15, r0 = (lane >> 4) * 16;
+      float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+      for (int r = 0; r < 16; ++r) {
+        const float* w = sW + S_LUW0 + (r0 + r) * 64;
+        s0 = fmaf(w[16 + c] - w[48 + c], sV[V_GC + r0 + r], s0);
+        s1 = fmaf(w[32 + c], sV[V_GWEFF + (r0 + r) * 16 + c], s1);
       }
-      sV[V_GHC + lane] = s;
+      float s = s0 + s1;
+      s += __shfl_xor_sync(0xffffffffu, s, 16);
+      if (lane < 16) sV[V_GHC + c] = s;
     }
   } else {
     if (tid < 512) gacc(gp, P_RD_W0 + tid, sV[V_GWEFF + tid]);
@@ -1320,19 +1347,6 @@ __device__ void graph_body(const StepArgs& a, const BlobHeader& hd, const GraphD
 #pragma unroll
     for (int r = 0; r < 16; ++r) t = fmaf(sW[S_QC + r * 16 + c], __shfl_sync(0xffffffffu, gqp, r), t);
     if (lane < 16) { sV[V_GHC + c] = t; sV[V_GQP + c] = gqp; }
-    __syncwarp();
-    for (int idx = lane; idx < 256; idx += 32) {
-      const int r = idx >> 4, cc = idx & 15;
-      gacc(gp, G_QC + idx, sV[V_GQP + r] * sV[V_HC + cc]);
-      gacc(gp, G_KC + idx, 0.25f * sV[V_QP + r] * sV[V_GSH + cc]);
-      gacc(gp, G_VC + idx, sV[V_GVP + r] * sV[V_HBAR + cc]);
-      gacc(gp, P_MHA_OUT_W + idx, sV[V_GSV + 48 + r] * sV[V_VP + cc]);
-    }
-    if (lane < 16) {
-      gacc(gp, G_QBC + lane, sV[V_GQP + lane]);
-      gacc(gp, G_VBC + lane, sV[V_GVP + lane]);
-      gacc(gp, P_MHA_OUT_B + lane, sV[V_GSV + 48 + lane]);
-    }
   }
   if (g.stage == 1) {   // road head feeds h^L of its candidate nodes directly
     for (int task = tid; task < k * 16; task += NT) {
@@ -1343,6 +1357,18 @@ __device__ void graph_body(const StepArgs& a, const BlobHeader& hd, const GraphD
   }
   __syncthreads();
   UPB_STAMP(14);
+  if (tid < 256) {   // composed-projection ("virtual") gradients, chained to the real tensors in k_reduce_finish
+    const int r = tid >> 4, cc = tid & 15;
+    gacc(gp, G_QC + tid, sV[V_GQP + r] * sV[V_HC + cc]);
+    gacc(gp, G_KC + tid, 0.25f * sV[V_QP + r] * sV[V_GSH + cc]);
+    gacc(gp, G_VC + tid, sV[V_GVP + r] * sV[V_HBAR + cc]);
+    gacc(gp, P_MHA_OUT_W + tid, sV[V_GSV + 48 + r] * sV[V_VP + cc]);
+  } else if (tid < 272) {
+    const int c = tid - 256;
+    gacc(gp, G_QBC + c, sV[V_GQP + c]);
+    gacc(gp, G_VBC + c, sV[V_GVP + c]);
+    gacc(gp, P_MHA_OUT_B + c, sV[V_GSV + 48 + c]);
+  }
 
   // ---- GCN layers, last to first
   for (int l = 1; l >= 0; --l) {

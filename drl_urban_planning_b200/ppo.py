@@ -75,6 +75,8 @@ class PPOUpdater:
         e = np.ones(T, np.float32) if exps is None else np.ascontiguousarray(exps, np.float32).reshape(T)
         self.exps_host = e
         self.exps = torch.as_tensor(e).to(self.device)
+        info = self.blob.info.astype(np.int64)
+        self._cost = 4 * info[:, 1] + info[:, 0]          # work estimate per graph (edges dominate)
         return self.blob
 
     # ------------------------------------------------------------------ pieces of update_params
@@ -118,12 +120,19 @@ class PPOUpdater:
         for epoch in range(self.opt_num_epochs):
             perm = np.arange(T)
             np.random.shuffle(perm)                                                    # :306-307
-            perm_dev = torch.as_tensor(perm.astype(np.int32)).to(self.device)
+            # this rank's shard of every minibatch, ordered for the kernel's static CTA schedule (long + short graph
+            # per CTA); one upload per epoch
+            shards = [self.engine.balance_ids(perm[i * B:(i + 1) * B][self.rank::self.world], self._cost)
+                      for i in range(nb)]
+            width = max((len(x) for x in shards), default=0)
+            ids_host = np.zeros((max(nb, 1), max(width, 1)), np.int32)
+            for i, x in enumerate(shards):
+                ids_host[i, :len(x)] = x
+            ids_dev = torch.as_tensor(ids_host).to(self.device)
             for i in range(nb):
                 sl = slice(i * B, min((i + 1) * B, T))
                 n_ind = int((self.exps_host[perm[sl]] != 0).sum())
-                ids = perm_dev[sl][self.rank::self.world].contiguous()
-                self.minibatch_step(ids, sl.stop - sl.start, n_ind)
+                self.minibatch_step(ids_dev[i, :len(shards[i])], sl.stop - sl.start, n_ind)
                 stats_all[i].copy_(self.grad[_lib.UPB_STAT_OFFSET:_lib.UPB_STAT_OFFSET + 8])
             st = stats_all[:nb].cpu().numpy().astype(np.float64)                       # one sync per epoch
             nB, nI = np.maximum(st[:, 3], 1), np.maximum(st[:, 4], 1)
