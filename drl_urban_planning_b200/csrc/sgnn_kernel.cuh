@@ -153,7 +153,7 @@ static_assert(HB_END <= NS * 32, "value/numeric weights + head-backward buffers 
 // per-CTA global scratch (floats): saved layer inputs + big-graph arrays
 __host__ __device__ inline size_t scratch_floats(int n_cap, int e_cap) {
   const size_t kcap = (size_t)(e_cap > n_cap ? e_cap : n_cap);
-  return (size_t)n_cap * (16 + 16 + 32 + 32 + 16 + 2) + kcap * 18 + 64;
+  return (size_t)n_cap * (16 + 16 + 32 + 32 + 32 + 16 + 2) + kcap * 18 + 64;
 }
 
 struct StepArgs {
@@ -984,8 +984,9 @@ __device__ void graph_body(const StepArgs& a, const BlobHeader& hd, const GraphD
   const int n = g.n, e = g.e, k = g.k;
   g.H0g = scr;
   g.H1g = scr + (size_t)a.n_cap * 16;
+  float* E0g = scr + (size_t)a.n_cap * 32;        // [n][32] saved EPQ of layer 0 (reloaded by the backward pass)
   if constexpr (BIG) {
-    float* b = scr + (size_t)a.n_cap * 32;
+    float* b = scr + (size_t)a.n_cap * 64;
     g.EPQ = b;  b += (size_t)a.n_cap * 32;
     g.GPQ = b;  b += (size_t)a.n_cap * 32;
     g.H = b;    b += (size_t)a.n_cap * 16;
@@ -1089,12 +1090,16 @@ __device__ void graph_body(const StepArgs& a, const BlobHeader& hd, const GraphD
   }
 
   // GCN layers (state_encoder.py:194-197): h <- h + (sum_{nbr} he) / (deg + eps), pull over the CSR
-  int exact_last = 0;
+  int exact_last = 0, exact_first = 0;
   for (int l = 0; l < 2; ++l) {
     const int bad = epq_phase(g, g.H, sW + (l == 0 ? S_WPQT0 : S_WPQT1), sW + (l == 0 ? S_B0 : S_B1));
     const int exact = __syncthreads_or(bad);     // any pre-activation outside the one-reciprocal range?
     UPB_STAMP(3+l*2);
     if (l == 1) exact_last = exact;
+    else exact_first = exact;
+    if (TRAIN && l == 0) {   // keep layer 0's EPQ for the backward pass (cheaper to reload than to recompute)
+      for (int i = tid; i < n * 8; i += NT) __stcg(reinterpret_cast<float4*>(E0g) + i, ld4(g.EPQ + i * 4));
+    }
     float4 msum = f4(0.f), hsum = f4(0.f);
     if (exact) pull_forward<true>(g, q, TRAIN && l == 0, g.H1g, l == 1, msum, hsum);
     else pull_forward<false>(g, q, TRAIN && l == 0, g.H1g, l == 1, msum, hsum);
@@ -1375,9 +1380,11 @@ __device__ void graph_body(const StepArgs& a, const BlobHeader& hd, const GraphD
     const float* Wpq = sW + (l == 0 ? S_WPQ0 : S_WPQ1);
     const float* hin = l == 0 ? g.H0g : g.H1g;     // layer input h^l (global scratch)
     int exact = exact_last;
-    if (l == 0) {   // EPQ of layer 0 was overwritten by layer 1: recompute from h^0
-      const int bad = epq_phase(g, hin, sW + S_WPQT0, sW + S_B0);
-      exact = __syncthreads_or(bad);
+    if (l == 0) {   // EPQ of layer 0 was overwritten by layer 1: reload the copy saved by the forward pass
+#pragma unroll 2
+      for (int i = tid; i < n * 8; i += NT) st4(g.EPQ + i * 4, __ldcg(reinterpret_cast<const float4*>(E0g) + i));
+      exact = exact_first;
+      __syncthreads();
       UPB_STAMP(17);
     }
     const bool last = (l == 1);
