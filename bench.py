@@ -288,6 +288,8 @@ def main():
         host_ret = torch.as_tensor(rng.standard_normal(BATCH).astype(np.float32)).pin_memory()
         host_fix = torch.full((BATCH,), -4.0).pin_memory()
         host_exp = torch.ones(BATCH).pin_memory()
+        host_side = torch.cat([torch.zeros(BATCH * 2), host_adv, host_ret, host_fix, host_exp]).pin_memory()
+        dev_side = torch.empty_like(host_side, device=dev)
         host_buf, dev_buf = None, None
         n_e2e = max(3, min(args.steps, 20))
         h2d = 0
@@ -299,8 +301,9 @@ def main():
             host_buf = b.host
             b.to(dev, out=dev_buf)
             dev_buf = b.dev
-            a_h = torch.as_tensor(actions[lo:lo + BATCH]).pin_memory()
-            d = [x.to(dev, non_blocking=True) for x in (a_h, host_adv, host_ret, host_fix, host_exp)]
+            host_side[:BATCH * 2].copy_(torch.from_numpy(actions[lo:lo + BATCH].reshape(-1)))   # into the pinned staging row
+            dev_side.copy_(host_side, non_blocking=True)               # actions | adv | ret | old log-probs | exps: one copy
+            d = [dev_side[:BATCH * 2]] + [dev_side[BATCH * (2 + j):BATCH * (3 + j)] for j in range(4)]
             eng.ppo_grad(b, params, d[0], d[1], d[2], d[3], d[4], 1.0 / gB, 1.0 / gI, out=grad)
             if world > 1:
                 dist.all_reduce(grad, op=dist.ReduceOp.SUM)

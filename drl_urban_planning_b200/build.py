@@ -33,7 +33,24 @@ def stale() -> bool:
     return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS)
 
 
+PYPTR = os.path.join(HERE, "_upb_pyptr.so")
+
+
+def build_pyptr(force: bool = False) -> str:
+    """Small CPython helper (host glue: pointer table of the state lists).  gcc only; optional at run time."""
+    import sysconfig
+    src = os.path.join(CSRC, "pyptr.c")
+    if not force and os.path.exists(PYPTR) and os.path.getmtime(PYPTR) >= os.path.getmtime(src):
+        return PYPTR
+    cmd = ["gcc", "-O2", "-shared", "-fPIC", "-I", sysconfig.get_paths()["include"], "-o", PYPTR, src]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("gcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+    return PYPTR
+
+
 def build_library(force: bool = False, verbose: bool = False) -> str:
+    build_pyptr(force)
     if not force and not stale():
         return LIB
     cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

@@ -1,0 +1,64 @@
+/* _upb_pyptr: pointer table of a list of reference-layout states, built with the CPython buffer protocol.
+ *
+ * `pack_states` needs 9 raw pointers per rollout state (include/upb200.h, upb_pack_fill).  Collecting them in
+ * Python costs ~1.5 us per array (2,304 arrays per 256-state minibatch); this helper walks the lists in C
+ * (~60 ns per array) and checks item size / contiguity on the way.  It is host glue only: no CUDA, no numpy headers.
+ *
+ *   pointer_table(states, out) -> -1 on success, or the index of the first state that needs the slow path
+ *     states : list/tuple of list/tuple of 9 objects exporting C-contiguous buffers
+ *     out    : writable buffer of 9 * len(states) uint64
+ */
+#define PY_SSIZE_T_CLEAN
+#include <Python.h>
+#include <stdint.h>
+
+static const Py_ssize_t kItem[9] = {4, 4, 8, 4, 1, 1, 1, 1, 4};   /* f32 f32 i64 f32 bool bool bool bool f32 */
+static const char kKind[9] = {'f', 'f', 'i', 'f', '?', '?', '?', '?', 'f'};
+
+static int kind_ok(const char* fmt, char want) {
+  if (!fmt) return 0;
+  while (*fmt == '<' || *fmt == '=' || *fmt == '@' || *fmt == '|') ++fmt;
+  switch (want) {
+    case 'f': return *fmt == 'f';
+    case 'i': return *fmt == 'q' || *fmt == 'l';
+    default: return *fmt == '?';
+  }
+}
+
+static PyObject* pointer_table(PyObject* self, PyObject* args) {
+  PyObject* states;
+  Py_buffer out;
+  if (!PyArg_ParseTuple(args, "Ow*", &states, &out)) return NULL;
+  PyObject* seq = PySequence_Fast(states, "states must be a sequence");
+  if (!seq) { PyBuffer_Release(&out); return NULL; }
+  const Py_ssize_t count = PySequence_Fast_GET_SIZE(seq);
+  long bad = -1;
+  if (out.len < (Py_ssize_t)(9 * count * sizeof(uint64_t))) {
+    PyBuffer_Release(&out);
+    Py_DECREF(seq);
+    PyErr_SetString(PyExc_ValueError, "pointer_table: output buffer too small");
+    return NULL;
+  }
+  uint64_t* dst = (uint64_t*)out.buf;
+  for (Py_ssize_t i = 0; i < count && bad < 0; ++i) {
+    PyObject* st = PySequence_Fast_GET_ITEM(seq, i);
+    if (!(PyList_Check(st) || PyTuple_Check(st)) || PySequence_Fast_GET_SIZE(st) != 9) { bad = (long)i; break; }
+    for (int j = 0; j < 9; ++j) {
+      PyObject* a = PySequence_Fast_GET_ITEM(st, j);
+      Py_buffer v;
+      if (PyObject_GetBuffer(a, &v, PyBUF_C_CONTIGUOUS | PyBUF_FORMAT) < 0) { PyErr_Clear(); bad = (long)i; break; }
+      const int ok = v.itemsize == kItem[j] && kind_ok(v.format, kKind[j]);
+      dst[9 * i + j] = (uint64_t)(uintptr_t)v.buf;
+      PyBuffer_Release(&v);         /* the caller's list keeps the array alive */
+      if (!ok) { bad = (long)i; break; }
+    }
+  }
+  PyBuffer_Release(&out);
+  Py_DECREF(seq);
+  return PyLong_FromLong(bad);
+}
+
+static PyMethodDef kMethods[] = {{"pointer_table", pointer_table, METH_VARARGS, "raw pointers of 9-array states"},
+                                 {NULL, NULL, 0, NULL}};
+static struct PyModuleDef kModule = {PyModuleDef_HEAD_INIT, "_upb_pyptr", NULL, -1, kMethods};
+PyMODINIT_FUNC PyInit__upb_pyptr(void) { return PyModule_Create(&kModule); }

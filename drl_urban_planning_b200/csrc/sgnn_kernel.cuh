@@ -449,6 +449,120 @@ struct GraphView {
   const int* cidx;         // [k]
 };
 
+// ---- tensor-core tiles for the dense per-node blocks (mma.sync m16n8k8 TF32, "3xTF32" error compensation) -------
+// fp32 parity (1e-4) rules out a single TF32 pass; splitting both operands into a TF32 head and a TF32 tail and
+// accumulating a_lo b_hi + a_hi b_lo + a_hi b_hi in fp32 gives ~2^-21 relative error per product.
+__device__ __forceinline__ uint32_t tf32_of(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void tf32_split(float x, uint32_t& hi, uint32_t& lo) {
+  hi = tf32_of(x);
+  lo = tf32_of(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                         uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+// one k-tile (8 columns) of a 16-row A tile held as four floats (rows g, g+8; tile columns t, t+4) times a B fragment
+// given as hi/lo pairs
+__device__ __forceinline__ void mma_3x(float (&c)[4], float a0, float a1, float a2, float a3, uint32_t bh0, uint32_t bh1,
+                                       uint32_t bl0, uint32_t bl1) {
+  uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
+  tf32_split(a0, h0, l0); tf32_split(a1, h1, l1); tf32_split(a2, h2, l2); tf32_split(a3, h3, l3);
+  mma_tf32(c, l0, l1, l2, l3, bh0, bh1);
+  mma_tf32(c, h0, h1, h2, h3, bl0, bl1);
+  mma_tf32(c, h0, h1, h2, h3, bh0, bh1);
+}
+
+// EPQ phase on the tensor cores: [n x 16] . WT[16 x 32], 16 nodes per warp-task.  The K dimension is permuted so
+// that each lane's A operands are ONE 128-bit row segment (lane (g, t) holds h[row][4t..4t+3]): k-tile "A" uses
+// k = 4t (tile column t) and 4t+1 (column t+4), k-tile "B" uses 4t+2 and 4t+3; the constant B fragments follow the
+// same permutation.  WT is [16 c][32 o].
+__device__ __forceinline__ int epq_phase_tc(const GraphView& g, const float* hsrc, const float* WT, const float* b) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int gq = lane >> 2, t = lane & 3;
+  uint32_t bh[4][4], bl[4][4];         // [n-tile][k index 4t + j]
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) tf32_split(WT[(4 * t + j) * 32 + nt * 8 + gq], bh[nt][j], bl[nt][j]);
+  float bias[4][2];
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt) {
+    bias[nt][0] = nt < 2 ? b[nt * 8 + 2 * t] : 0.f;
+    bias[nt][1] = nt < 2 ? b[nt * 8 + 2 * t + 1] : 0.f;
+  }
+  float amax = 0.f;
+  const int n = g.n;
+  for (int m0 = warp * 16; m0 < n; m0 += NW * 16) {
+    const int r0 = min(m0 + gq, n - 1), r1 = min(m0 + gq + 8, n - 1);
+    const float4 v = ld4(hsrc + r0 * 16 + 4 * t), w = ld4(hsrc + r1 * 16 + 4 * t);
+    float acc[4][4];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      acc[nt][0] = bias[nt][0]; acc[nt][1] = bias[nt][1]; acc[nt][2] = bias[nt][0]; acc[nt][3] = bias[nt][1];
+      mma_3x(acc[nt], v.x, w.x, v.y, w.y, bh[nt][0], bh[nt][1], bl[nt][0], bl[nt][1]);
+      mma_3x(acc[nt], v.z, w.z, v.w, w.w, bh[nt][2], bh[nt][3], bl[nt][2], bl[nt][3]);
+    }
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      amax = fmaxf(amax, fmaxf(fmaxf(fabsf(acc[nt][0]), fabsf(acc[nt][1])), fmaxf(fabsf(acc[nt][2]), fabsf(acc[nt][3]))));
+      if (m0 + gq < n)
+        *reinterpret_cast<float2*>(g.EPQ + (m0 + gq) * 32 + nt * 8 + 2 * t) = make_float2(exp2a(acc[nt][0]), exp2a(acc[nt][1]));
+      if (m0 + gq + 8 < n)
+        *reinterpret_cast<float2*>(g.EPQ + (m0 + gq + 8) * 32 + nt * 8 + 2 * t) = make_float2(exp2a(acc[nt][2]), exp2a(acc[nt][3]));
+    }
+  }
+  return !(amax <= 10.9f);      // also true for NaN
+}
+
+// g_h = g_h' + GPQ . Wpq on the tensor cores, in place over H (which holds gs = g_h' / (deg + eps)); 16 nodes per
+// warp-task, K = 32 permuted as above (two 128-bit row segments per row).  Wpq is [32 o][16 c].  If `rescale`, the
+// result is stored scaled by 1 / (deg + eps) again (the next pull wants that form).
+__device__ __forceinline__ void gh_phase_tc(const GraphView& g, const float* Wpq, bool rescale) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int gq = lane >> 2, t = lane & 3;
+  uint32_t bh[2][8], bl[2][8];         // [n-tile][k index: j<4 -> 4t+j, j>=4 -> 16+4t+(j-4)]
+#pragma unroll
+  for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = (j < 4 ? 0 : 16) + 4 * t + (j & 3);
+      tf32_split(Wpq[k * 16 + nt * 8 + gq], bh[nt][j], bl[nt][j]);
+    }
+  const int n = g.n;
+  for (int m0 = warp * 16; m0 < n; m0 += NW * 16) {
+    const int r0 = min(m0 + gq, n - 1), r1 = min(m0 + gq + 8, n - 1);
+    const float4 v0 = ld4(g.GPQ + r0 * 32 + 4 * t), v1 = ld4(g.GPQ + r0 * 32 + 16 + 4 * t);
+    const float4 w0 = ld4(g.GPQ + r1 * 32 + 4 * t), w1 = ld4(g.GPQ + r1 * 32 + 16 + 4 * t);
+    const float rd0 = (float)(g.rp[r0 + 1] - g.rp[r0]) + EPS_DEG, rd1 = (float)(g.rp[r1 + 1] - g.rp[r1]) + EPS_DEG;
+    float acc[2][4];
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt) {
+      const float2 h0 = *reinterpret_cast<const float2*>(g.H + r0 * 16 + nt * 8 + 2 * t);
+      const float2 h1 = *reinterpret_cast<const float2*>(g.H + r1 * 16 + nt * 8 + 2 * t);
+      acc[nt][0] = h0.x * rd0; acc[nt][1] = h0.y * rd0; acc[nt][2] = h1.x * rd1; acc[nt][3] = h1.y * rd1;
+      mma_3x(acc[nt], v0.x, w0.x, v0.y, w0.y, bh[nt][0], bh[nt][1], bl[nt][0], bl[nt][1]);
+      mma_3x(acc[nt], v0.z, w0.z, v0.w, w0.w, bh[nt][2], bh[nt][3], bl[nt][2], bl[nt][3]);
+      mma_3x(acc[nt], v1.x, w1.x, v1.y, w1.y, bh[nt][4], bh[nt][5], bl[nt][4], bl[nt][5]);
+      mma_3x(acc[nt], v1.z, w1.z, v1.w, w1.w, bh[nt][6], bh[nt][7], bl[nt][6], bl[nt][7]);
+    }
+    const float s0 = rescale ? g.inv[r0] : 1.f, s1 = rescale ? g.inv[r1] : 1.f;
+    __syncwarp();                                   // every lane has read its H inputs before any lane overwrites
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt) {
+      if (m0 + gq < n)
+        *reinterpret_cast<float2*>(g.H + (m0 + gq) * 16 + nt * 8 + 2 * t) = make_float2(acc[nt][0] * s0, acc[nt][1] * s0);
+      if (m0 + gq + 8 < n)
+        *reinterpret_cast<float2*>(g.H + (m0 + gq + 8) * 16 + nt * 8 + 2 * t) = make_float2(acc[nt][2] * s1, acc[nt][3] * s1);
+    }
+  }
+}
+
 // exp-transformed edge-MLP pre-activations of one layer: EPQ[i][o] = exp(2 (Wpq[o] . h_i + b[o]))  (b only for o<16).
 // 8 lanes per node PAIR, 4 outputs per lane.  Each lane keeps its 16x4 slice of the transposed weights WT[c][o] in
 // registers for the whole phase (64 floats), so a pair costs only the 8 row loads of the two h vectors.
@@ -1092,6 +1206,7 @@ __device__ void graph_body(const StepArgs& a, const BlobHeader& hd, const GraphD
   // GCN layers (state_encoder.py:194-197): h <- h + (sum_{nbr} he) / (deg + eps), pull over the CSR
   int exact_last = 0, exact_first = 0;
   for (int l = 0; l < 2; ++l) {
+    // (epq_phase_tc, the 3xTF32 mma.sync variant, measured no faster than the packed-FMA one: profiles/)
     const int bad = epq_phase(g, g.H, sW + (l == 0 ? S_WPQT0 : S_WPQT1), sW + (l == 0 ? S_B0 : S_B1));
     const int exact = __syncthreads_or(bad);     // any pre-activation outside the one-reciprocal range?
     UPB_STAMP(3+l*2);
@@ -1424,38 +1539,7 @@ __device__ void graph_body(const StepArgs& a, const BlobHeader& hd, const GraphD
       for (int x = 0; x < 4; ++x)
         st4(redbuf + warp * 512 + (to * 4 + x) * 16 + tc * 4, make_float4(acc[x][0], acc[x][1], acc[x][2], acc[x][3]));
     }
-    {   // g_h = g_h' + GPQ Wpq (residual), in place.  8 lanes per node pair, 2 output channels per lane; the lane's
-        // 32x2 slice of Wpq lives in registers, so a pair costs the 16 row loads of its two GPQ rows.
-      const int og = tid & 7;
-      float2 w2[32];
-#pragma unroll
-      for (int o = 0; o < 32; ++o) w2[o] = *reinterpret_cast<const float2*>(Wpq + o * 16 + og * 2);
-      const int npair = (n + 1) >> 1;
-      for (int task = tid; task < npair * 8; task += NT) {
-        const int i0 = (task >> 3) * 2, i1 = min(i0 + 1, n - 1);
-        // H holds gs = g_h' / (deg + eps): undo the scaling for the residual term
-        const float rd0 = (float)(g.rp[i0 + 1] - g.rp[i0]) + EPS_DEG, rd1 = (float)(g.rp[i1 + 1] - g.rp[i1]) + EPS_DEG;
-        float2 s0 = *reinterpret_cast<const float2*>(g.H + i0 * 16 + og * 2);
-        float2 s1 = *reinterpret_cast<const float2*>(g.H + i1 * 16 + og * 2);
-        s0.x *= rd0; s0.y *= rd0; s1.x *= rd1; s1.y *= rd1;
-#pragma unroll
-        for (int o4 = 0; o4 < 8; ++o4) {
-          const float4 ga = ld4(g.GPQ + i0 * 32 + o4 * 4), gb = ld4(g.GPQ + i1 * 32 + o4 * 4);
-#pragma unroll
-          for (int x = 0; x < 4; ++x) {
-            const float xa = comp(ga, x), xb = comp(gb, x);
-            s0 = __ffma2_rn(w2[o4 * 4 + x], make_float2(xa, xa), s0);
-            s1 = __ffma2_rn(w2[o4 * 4 + x], make_float2(xb, xb), s1);
-          }
-        }
-        if (l == 1) {        // the next (lower) layer's pull wants the scaled form again
-          const float v0 = g.inv[i0], v1 = g.inv[i1];
-          s0.x *= v0; s0.y *= v0; s1.x *= v1; s1.y *= v1;
-        }
-        *reinterpret_cast<float2*>(g.H + i0 * 16 + og * 2) = s0;
-        if (i1 != i0) *reinterpret_cast<float2*>(g.H + i1 * 16 + og * 2) = s1;
-      }
-    }
+    gh_phase_tc(g, Wpq, l == 1);     // g_h = g_h' + GPQ Wpq (residual), in place
     __syncthreads();
     if (tid < 512) {
       const float* redbuf = smem + S_EPQ;

@@ -28,10 +28,18 @@ def _as_numpy(a, want):
     return a
 
 
+try:                                   # C helper (csrc/pyptr.c); the pure-Python loop below is the fallback
+    from . import _upb_pyptr as _pyptr
+except ImportError:                    # pragma: no cover
+    _pyptr = None
+
+
 def _pointer_table(states: Sequence[Sequence]):
     n = len(states)
     ptrs = np.empty(9 * n, dtype=np.uint64)
     keep = []
+    if _pyptr is not None and _pyptr.pointer_table(states, ptrs) < 0:
+        return ptrs, keep              # every array was already a C-contiguous buffer of the right item type
     k = 0
     for st in states:
         if len(st) != 9:
