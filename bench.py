@@ -290,7 +290,9 @@ def main():
         host_exp = torch.ones(BATCH).pin_memory()
         host_side = torch.cat([torch.zeros(BATCH * 2), host_adv, host_ret, host_fix, host_exp]).pin_memory()
         dev_side = torch.empty_like(host_side, device=dev)
-        host_buf, dev_buf = None, None
+        # pinned staging buffer with headroom: minibatches differ a little in size; a refill never re-measures
+        host_buf = torch.empty(int(blob.nbytes / args.pool * 1.3), dtype=torch.uint8).pin_memory()
+        dev_buf = torch.empty(host_buf.numel(), dtype=torch.uint8, device=dev)
         n_e2e = max(3, min(args.steps, 20))
         h2d = 0
 

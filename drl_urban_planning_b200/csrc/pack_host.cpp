@@ -94,8 +94,10 @@ struct Plan {
 
 template <class F>
 void parallel_for(int count, int threads, F&& fn) {
-  if (threads <= 0) threads = (int)std::max(1u, std::thread::hardware_concurrency());
-  threads = std::min(threads, std::max(1, count / 8));
+  // spawning a thread costs tens of microseconds: a handful of them saturates the memory system for this copy-bound
+  // work, a hundred (hardware_concurrency on a big host) would cost more than the packing itself
+  if (threads <= 0) threads = (int)std::min(12u, std::max(1u, std::thread::hardware_concurrency()));
+  threads = std::min(threads, std::max(1, count / 16));
   if (threads <= 1) {
     for (int i = 0; i < count; ++i) fn(i);
     return;

@@ -54,6 +54,11 @@ def _pointer_table(states: Sequence[Sequence]):
     return ptrs, keep
 
 
+def torch_int64():
+    import torch
+    return torch.int64
+
+
 def infer_caps(states: Sequence[Sequence]):
     st = states[0]
     return int(np.shape(st[1])[0]), int(np.shape(st[2])[0])
@@ -115,6 +120,16 @@ def pack_states(states: Sequence[Sequence], n_cap: Optional[int] = None, e_cap: 
         n_cap, e_cap = infer_caps(states)
     L = _lib.lib()
     ptrs, keep = _pointer_table(states)
+    if out_host is not None:
+        # reuse the caller's (pinned) buffer: fill straight away, the blob header tells how many bytes were used;
+        # only a too-small buffer costs the extra measuring pass below
+        cap = int(out_host.numel())
+        rc = L.upb_pack_fill(len(states), ptrs.ctypes.data, n_cap, e_cap, threads, out_host.data_ptr(), cap)
+        if rc == 0:
+            nb = int(out_host[16:24].view(torch_int64()).item())          # BlobHeader.total_bytes
+            return PackedGraphs(out_host, nb, len(states), n_cap, e_cap)
+        if rc != -4:                                                       # anything but UPB_ERR_CAPACITY
+            _lib.check(rc, "upb_pack_fill")
     nbytes = C.c_uint64()
     _lib.check(L.upb_pack_measure(len(states), ptrs.ctypes.data, n_cap, e_cap, threads, C.byref(nbytes)),
                "upb_pack_measure")
