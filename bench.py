@@ -216,7 +216,7 @@ def main():
     pert = params * (1.0 + 0.05 * torch.randn(params.shape, device=dev, generator=torch.Generator(dev).manual_seed(3)))
     _, fixed, _ = eng.forward(blob, pert, act)
     info = blob.info.astype(np.int64)
-    cost = 4 * info[:, 1] + info[:, 0]
+    cost = Engine.graph_cost(info)      # cycles model fitted to tools/phase_times.py
     mb_ids = []
     for m in range(args.pool):
         ids = np.arange(m * BATCH, (m + 1) * BATCH)
@@ -290,27 +290,38 @@ def main():
         host_exp = torch.ones(BATCH).pin_memory()
         host_side = torch.cat([torch.zeros(BATCH * 2), host_adv, host_ret, host_fix, host_exp]).pin_memory()
         dev_side = torch.empty_like(host_side, device=dev)
-        # pinned staging buffer with headroom: minibatches differ a little in size; a refill never re-measures
-        host_buf = torch.empty(int(blob.nbytes / args.pool * 1.3), dtype=torch.uint8).pin_memory()
-        dev_buf = torch.empty(host_buf.numel(), dtype=torch.uint8, device=dev)
+        # Two pinned staging buffers (with headroom, so a refill never re-measures): while the GPU works on step i the
+        # host packer (C, releases the GIL) fills the buffer of step i+1.  Every step's blob and per-sample arrays still
+        # cross PCIe inside the timed region and every step ends with a D2H read of its losses.
+        from concurrent.futures import ThreadPoolExecutor
+        cap = int(blob.nbytes / args.pool * 1.3)
+        host_bufs = [torch.empty(cap, dtype=torch.uint8).pin_memory() for _ in range(2)]
+        side_bufs = [host_side.clone().pin_memory() for _ in range(2)]
+        dev_buf = torch.empty(cap, dtype=torch.uint8, device=dev)
         n_e2e = max(3, min(args.steps, 20))
         h2d = 0
+        pool_ex = ThreadPoolExecutor(1)
+
+        def pack_job(i):
+            lo = (i % args.pool) * BATCH
+            b = pk(states[lo:lo + BATCH], blob.n_cap, blob.e_cap, out_host=host_bufs[i & 1])
+            side_bufs[i & 1][:BATCH * 2].copy_(torch.from_numpy(actions[lo:lo + BATCH].reshape(-1)))
+            return b
+
+        pending = {0: pool_ex.submit(pack_job, 0)}
 
         def e2e_step(i):
-            nonlocal host_buf, dev_buf, h2d
-            lo = (i % args.pool) * BATCH
-            b = pk(states[lo:lo + BATCH], blob.n_cap, blob.e_cap, out_host=host_buf)
-            host_buf = b.host
+            nonlocal h2d
+            b = pending.pop(i).result()
             b.to(dev, out=dev_buf)
-            dev_buf = b.dev
-            host_side[:BATCH * 2].copy_(torch.from_numpy(actions[lo:lo + BATCH].reshape(-1)))   # into the pinned staging row
-            dev_side.copy_(host_side, non_blocking=True)               # actions | adv | ret | old log-probs | exps: one copy
+            dev_side.copy_(side_bufs[i & 1], non_blocking=True)      # actions | adv | ret | old log-probs | exps: one copy
             d = [dev_side[:BATCH * 2]] + [dev_side[BATCH * (2 + j):BATCH * (3 + j)] for j in range(4)]
             eng.ppo_grad(b, params, d[0], d[1], d[2], d[3], d[4], 1.0 / gB, 1.0 / gI, out=grad)
             if world > 1:
                 dist.all_reduce(grad, op=dist.ReduceOp.SUM)
             eng.apply(params, grad)
-            eng.read_losses(grad)                     # D2H of the step's result
+            pending[i + 1] = pool_ex.submit(pack_job, i + 1)          # overlaps with the GPU work just queued
+            eng.read_losses(grad)                                     # D2H of the step's result (synchronises)
             h2d = b.nbytes + 4 * (BATCH * 2 + BATCH * 4)
 
         for i in range(2):
@@ -321,11 +332,14 @@ def main():
             e2e_step(2 + i)
         barrier()
         dt = torch.tensor([time.perf_counter() - t1], device=dev)
+        pending.popitem()[1].result()
+        pool_ex.shutdown()
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         e2e = {"value": BATCH * world * n_e2e / float(dt.item()), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": 32, "steps": n_e2e,
-               "path": "reference-layout host states -> upb_pack_fill -> pinned -> H2D -> upb_ppo_grad/upb_apply -> D2H losses"}
+               "path": "reference-layout host states -> upb_pack_fill -> pinned (double-buffered, packer thread overlaps the GPU) "
+                       "-> H2D -> upb_ppo_grad/upb_apply -> D2H losses"}
 
     # ---- CPU baseline beside it (rank 0, N=1): oracle port of the reference's padded eager dataflow
     cpu = None

@@ -176,7 +176,7 @@ struct StepArgs {
   float* scratch;      // [gridDim.x][scratch_stride]
   size_t scratch_stride;
   int n_cap, e_cap;
-  long long* stamps;   // optional [64] clock64() phase stamps of the first graph of CTA 0 (tools/phase_times.py)
+  long long* stamps;   // optional [384]: [0,64) clock64() phase stamps, [64,224) busy cycles per CTA, [224,384) prologue cycles; of the first graph of CTA 0 (tools/phase_times.py)
 };
 
 // ---- small device helpers ------------------------------------------------------------------------------
@@ -1607,6 +1607,7 @@ __device__ void graph_body(const StepArgs& a, const BlobHeader& hd, const GraphD
 template <bool TRAIN>
 __global__ void __launch_bounds__(NT, 1) k_sgnn(const __grid_constant__ StepArgs a) {
   extern __shared__ __align__(16) float smem[];
+  const long long t_cta0 = a.stamps ? clock64() : 0;
   load_weights(a.params, smem);
   float* gp = nullptr;
   if constexpr (TRAIN) {
@@ -1614,6 +1615,7 @@ __global__ void __launch_bounds__(NT, 1) k_sgnn(const __grid_constant__ StepArgs
     for (int i = threadIdx.x; i < G_ROW; i += NT) gp[i] = 0.f;
   }
   __syncthreads();
+  if (a.stamps && threadIdx.x == 0 && blockIdx.x < 160) a.stamps[64 + 160 + blockIdx.x] = clock64() - t_cta0;   // launch prologue
   const BlobHeader& hd = *reinterpret_cast<const BlobHeader*>(a.blob);
   const GraphDesc* descs = reinterpret_cast<const GraphDesc*>(a.blob + hd.off_desc);
   float* scr = a.scratch + (size_t)blockIdx.x * a.scratch_stride;
@@ -1649,6 +1651,7 @@ __global__ void __launch_bounds__(NT, 1) k_sgnn(const __grid_constant__ StepArgs
     else graph_body<TRAIN, false>(a, hd, d, gid, smem, gp, scr, item == (int)blockIdx.x);
     __syncthreads();
   }
+  if (a.stamps && threadIdx.x == 0 && blockIdx.x < 160) a.stamps[64 + blockIdx.x] = clock64() - t_cta0;           // CTA busy time
 }
 
 }  // namespace upb

@@ -151,18 +151,37 @@ class Engine:
     def grid(self) -> int:
         return int(_lib.lib().upb_grid_size(self._ctx))
 
+    @staticmethod
+    def graph_cost(info: np.ndarray) -> np.ndarray:
+        """Estimated cycles of one graph in the fused training kernel from (n, e, k, stage) rows
+        (fit to tools/phase_times.py: pulls ~ 22 / edge, node phases ~ 146 / node, head ~ 150 / candidate)."""
+        i = np.asarray(info, dtype=np.int64)
+        return 22 * i[:, 1] + 146 * i[:, 0] + 150 * i[:, 2] + 15000
+
     def balance_ids(self, ids: np.ndarray, cost: np.ndarray) -> np.ndarray:
-        """Order graph ids for the kernel's static schedule (ids[i] -> CTA i % grid, round i // grid): sort by cost,
-        longest first, and reverse every second round so each CTA pairs a long graph with a short one."""
+        """Order graph ids for the kernel's static schedule (ids[i] -> CTA i % grid, round i // grid).
+        Longest-processing-time-first: graphs in descending cost go to the least loaded CTA; CTAs are then numbered by
+        how many graphs they hold (round r must cover CTAs 0..len_r-1), so e.g. with 256 graphs on 148 SMs the 40
+        largest graphs run alone and the other 216 are paired long + short."""
+        import heapq
         ids = np.asarray(ids)
-        order = ids[np.argsort(-np.asarray(cost)[ids], kind="stable")]
         g = self.grid
-        out = order.copy()
-        for r in range(1, (len(order) + g - 1) // g, 2):
-            seg = order[r * g:(r + 1) * g]
-            # a partial last round is aligned to the END of the CTA range, then reversed: CTA 0 (longest) gets the shortest
-            out[r * g:r * g + len(seg)] = seg[::-1]
-        return out
+        if len(ids) <= g:
+            return ids[np.argsort(-np.asarray(cost)[ids], kind="stable")]
+        c = np.asarray(cost, dtype=np.float64)[ids]
+        order = np.argsort(-c, kind="stable")
+        bins = [[] for _ in range(g)]
+        heap = [(0.0, b) for b in range(g)]
+        for k in order:
+            load, b = heapq.heappop(heap)
+            bins[b].append(int(ids[k]))
+            heapq.heappush(heap, (load + float(c[k]), b))
+        bins.sort(key=lambda x: -len(x))
+        out = []
+        for r in range(len(bins[0])):
+            row = [b[r] for b in bins if len(b) > r]
+            out.extend(row)
+        return np.asarray(out, dtype=ids.dtype)
 
     def set_stamp_buffer(self, buf: Optional[torch.Tensor]) -> None:
         """int64[64] device tensor receiving clock64() phase stamps (debug), or None."""

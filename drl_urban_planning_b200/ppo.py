@@ -76,7 +76,7 @@ class PPOUpdater:
         self.exps_host = e
         self.exps = torch.as_tensor(e).to(self.device)
         info = self.blob.info.astype(np.int64)
-        self._cost = 4 * info[:, 1] + info[:, 0]          # work estimate per graph (edges dominate)
+        self._cost = Engine.graph_cost(info)
         return self.blob
 
     # ------------------------------------------------------------------ pieces of update_params

@@ -150,7 +150,7 @@ int upb_profile_read(upb_ctx* ctx, double* total_ms, int* launches);
  * CTA i % grid in round i / grid, so callers can balance the static schedule (see PPOUpdater.balance_ids). */
 int upb_grid_size(const upb_ctx* ctx);
 
-/* Debug: device int64[64] that receives clock64() stamps at the phase boundaries of the first graph walked by CTA 0
+/* Debug: device int64[384] that receives clock64() stamps (phases of one graph, busy cycles per CTA) at the phase boundaries of the first graph walked by CTA 0
  * of every following fused-kernel launch (NULL switches it off).  See tools/phase_times.py. */
 int upb_set_stamp_buffer(upb_ctx* ctx, void* stamps_dev);
 

@@ -20,12 +20,14 @@ t = lambda x: torch.as_tensor(x, device=dev)
 adv, ret, exps = synth.make_ppo_targets(1, count)
 fixed = np.full((count, 1), -4.0, np.float32)
 params = t(PL.default_init(1))
-stamps = torch.zeros(64, dtype=torch.int64, device=dev)
+stamps = torch.zeros(384, dtype=torch.int64, device=dev)
+info = blob.info.astype(np.int64)
+ids = t(eng.balance_ids(np.arange(count), Engine.graph_cost(info)).astype(np.int32))
 args = (blob, params, t(actions), t(adv), t(ret), t(fixed), t(exps), 1.0 / count, 1.0 / count)
 for _ in range(3):
-    eng.ppo_grad(*args)
+    eng.ppo_grad(*args, ids=ids)
 eng.set_stamp_buffer(stamps)
-eng.ppo_grad(*args)
+eng.ppo_grad(*args, ids=ids)
 torch.cuda.synchronize()
 st = stamps.cpu().numpy()
 print("graph 0: n, e, k, stage =", blob.info[0])
@@ -35,3 +37,6 @@ for i in [1, 2, 3, 4, 5, 6, 7, 8, 9, 20, 10, 11, 12, 14, 15, 16, 17, 18, 19, 21]
     print(f"{i:3d} {NAMES.get(i, ''):28s} {st[i] - prev:8d} cycles  {100.0 * (st[i] - prev) / tot:5.1f}%")
     prev = st[i]
 print("total", tot, "cycles")
+busy = st[64:64 + eng.grid]; pro = st[224:224 + eng.grid]
+print(f"per-CTA busy cycles: max {busy.max()}  mean {busy.mean():.0f}  min {busy.min()}  (balance {busy.mean() / busy.max():.2f});"
+      f" launch prologue mean {pro.mean():.0f} max {pro.max()}")
