@@ -1647,8 +1647,8 @@ __global__ void __launch_bounds__(NT, 1) k_sgnn(const __grid_constant__ StepArgs
       }
     }
     const bool big = d.n > NS || 2 * d.e > AS || d.k > KS || d.ord_rounds > ORD_ROUNDS;
-    if (big) graph_body<TRAIN, true>(a, hd, d, gid, smem, gp, scr, item == (int)blockIdx.x);
-    else graph_body<TRAIN, false>(a, hd, d, gid, smem, gp, scr, item == (int)blockIdx.x);
+    if (big) graph_body<TRAIN, true>(a, hd, d, gid, smem, gp, scr, item == (int)(blockIdx.x + gridDim.x));   // stamps: the SECOND graph of CTA 0 (steady state)
+    else graph_body<TRAIN, false>(a, hd, d, gid, smem, gp, scr, item == (int)(blockIdx.x + gridDim.x));   // stamps: the SECOND graph of CTA 0 (steady state)
     __syncthreads();
   }
   if (a.stamps && threadIdx.x == 0 && blockIdx.x < 160) a.stamps[64 + blockIdx.x] = clock64() - t_cta0;           // CTA busy time

@@ -105,11 +105,12 @@ class PPOUpdater:
         self.load_states(states, actions, exps)
         T = self.blob.count
         dev = self.device
-        values, _, _ = self.forward_all()                                             # :256-264
+        # one no-grad sweep yields both pre-pass results of the reference: values (:256-264) and the fixed
+        # log-probs (:283-292); neither depends on the other
+        values, self.fixed_log_probs, _ = self.forward_all()
         rewards_t = torch.as_tensor(np.ascontiguousarray(rewards, np.float32)).reshape(T).to(dev)
         masks_t = torch.as_tensor(np.ascontiguousarray(masks, np.float32)).reshape(T).to(dev)
         self.advantages, self.returns = self.engine.gae(rewards_t, masks_t, values, self.gamma, self.tau)  # :267
-        _, self.fixed_log_probs, _ = self.forward_all()                               # :283-292
         return self.update_policy(iteration, log_fn)
 
     def update_policy(self, iteration: int = 0, log_fn=None):
