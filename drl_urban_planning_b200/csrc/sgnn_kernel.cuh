@@ -366,64 +366,74 @@ __device__ __forceinline__ void matvec8(const float* __restrict__ W, const float
 
 // ---- once per launch: parameters -> shared memory (with the composed attention projections) --------------
 __device__ __forceinline__ void load_weights(const float* __restrict__ P, float* sW) {
+  // Every global load is issued before the first shared store (one L2/HBM round trip per launch, not one per loop).
   const int t = threadIdx.x;
-  for (int i = t; i < 384; i += NT) {
-    const int f = i >> 4, c = i & 15;
-    sW[S_WET + i] = f < F ? P[P_ENC_W + c * F + f] : 0.f;
+  static_assert(NT == 512, "load_weights is laid out for 512 threads");
+  const int o = t >> 4, c = t & 15;
+  const int src = o < 16 ? o * 32 + c : (o - 16) * 32 + 16 + c;          // (P | Q) split of a gcn weight row
+  const float wet = (t < 384 && (t >> 4) < F) ? __ldg(P + P_ENC_W + c * F + (t >> 4)) : 0.f;
+  const float g0 = __ldg(P + P_GCN0_W + src), g1 = __ldg(P + P_GCN1_W + src);
+  const float in0 = __ldg(P + P_MHA_IN_W + t), in1 = t < 256 ? __ldg(P + P_MHA_IN_W + 512 + t) : 0.f;
+  float wq = 0.f, wk = 0.f, wv = 0.f, wo = 0.f;
+  if (t < 256) {
+    wq = __ldg(P + P_ATT_Q_W + t); wk = __ldg(P + P_ATT_K_W + t); wv = __ldg(P + P_ATT_V_W + t);
+    wo = __ldg(P + P_MHA_OUT_W + t);
   }
-  if (t < 16) sW[S_BE + t] = P[P_ENC_B + t];
-  for (int i = t; i < 512; i += NT) {
-    const int o = i >> 4, c = i & 15;
-    const int src = o < 16 ? o * 32 + c : (o - 16) * 32 + 16 + c;
-    sW[S_WPQ0 + i] = P[P_GCN0_W + src];
-    sW[S_WPQ1 + i] = P[P_GCN1_W + src];
-    sW[S_WPQT0 + c * 32 + o] = P[P_GCN0_W + src];
-    sW[S_WPQT1 + c * 32 + o] = P[P_GCN1_W + src];
+  float lu[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) lu[j] = __ldg(P + P_LU_W0 + t + NT * j);
+  const float rd = __ldg(P + P_RD_W0 + t);
+  float sm0 = 0.f, sm1 = 0.f, sm2 = 0.f;     // small vectors, one element per thread group
+  if (t < 16) { sm0 = __ldg(P + P_ENC_B + t); sm1 = __ldg(P + P_GCN0_B + t); sm2 = __ldg(P + P_GCN1_B + t); }
+  else if (t < 32) { sm0 = __ldg(P + P_MHA_OUT_B + t - 16); sm1 = __ldg(P + P_ATT_Q_B + t - 16); sm2 = __ldg(P + P_ATT_V_B + t - 16); }
+  else if (t < 64) { sm0 = __ldg(P + P_LU_B0 + t - 32); sm1 = __ldg(P + P_LU_W1 + t - 32); }
+  else if (t < 96) { sm0 = __ldg(P + P_RD_B0 + t - 64); sm1 = __ldg(P + P_RD_W1 + t - 64); }
+  else if (t < 112) { sm0 = __ldg(P + P_MHA_IN_B + t - 96); sm1 = __ldg(P + P_MHA_IN_B + 32 + t - 96); }
+
+  float* tmp = sW + S_EPQ;                   // staging (the EPQ region is idle at launch time):
+                                             // in_proj_weight [48][16] | Wq | Wk | Wv | bq | bv | bin_q | bin_v
+  if (t < 384) sW[S_WET + t] = wet;
+  sW[S_WPQ0 + t] = g0; sW[S_WPQ1 + t] = g1;
+  sW[S_WPQT0 + c * 32 + o] = g0; sW[S_WPQT1 + c * 32 + o] = g1;
+  tmp[t] = in0;
+  if (t < 256) {
+    tmp[512 + t] = in1;
+    tmp[768 + t] = wq; tmp[1024 + t] = wk; tmp[1280 + t] = wv;
+    sW[S_WO + t] = wo;
+    sW[S_WOT + c * 16 + o] = wo;
   }
-  if (t < 16) {
-    sW[S_B0 + t] = P[P_GCN0_B + t];
-    sW[S_B1 + t] = P[P_GCN1_B + t];
-    sW[S_BO + t] = P[P_MHA_OUT_B + t];
-  }
-  for (int i = t; i < 256; i += NT) {
-    const int r = i >> 4, c = i & 15;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) sW[S_LUW0 + t + NT * j] = lu[j];
+  sW[S_RDW0 + t] = rd;
+  sW[S_RDW0T + c * 32 + o] = rd;
+  if (t < 16) { sW[S_BE + t] = sm0; sW[S_B0 + t] = sm1; sW[S_B1 + t] = sm2; }
+  else if (t < 32) { sW[S_BO + t - 16] = sm0; tmp[1536 + t - 16] = sm1; tmp[1552 + t - 16] = sm2; }
+  else if (t < 64) { sW[S_LUB0 + t - 32] = sm0; sW[S_LUW1 + t - 32] = sm1; }
+  else if (t < 96) { sW[S_RDB0 + t - 64] = sm0; sW[S_RDW1 + t - 64] = sm1; }
+  else if (t < 112) { tmp[1568 + t - 96] = sm0; tmp[1584 + t - 96] = sm1; }
+  __syncthreads();
+  // composed attention projections: Qc = Win_q Wq, Kc = Win_k Wk, Vc = Win_v Wv (+ transposes), qbc, vbc
+  if (t < 256) {
     float q = 0.f, k = 0.f, v = 0.f;
-#pragma unroll 4
+#pragma unroll
     for (int m = 0; m < 16; ++m) {
-      q = fmaf(P[P_MHA_IN_W + r * 16 + m], P[P_ATT_Q_W + m * 16 + c], q);
-      k = fmaf(P[P_MHA_IN_W + (16 + r) * 16 + m], P[P_ATT_K_W + m * 16 + c], k);
-      v = fmaf(P[P_MHA_IN_W + (32 + r) * 16 + m], P[P_ATT_V_W + m * 16 + c], v);
+      q = fmaf(tmp[o * 16 + m], tmp[768 + m * 16 + c], q);
+      k = fmaf(tmp[(16 + o) * 16 + m], tmp[1024 + m * 16 + c], k);
+      v = fmaf(tmp[(32 + o) * 16 + m], tmp[1280 + m * 16 + c], v);
     }
-    sW[S_QC + i] = q;
-    sW[S_KC + i] = k;
-    sW[S_VC + i] = v;
-    sW[S_WO + i] = P[P_MHA_OUT_W + i];
-    const int tr = c * 16 + r;
-    sW[S_QCT + tr] = q;
-    sW[S_KCT + tr] = k;
-    sW[S_VCT + tr] = v;
-    sW[S_WOT + tr] = P[P_MHA_OUT_W + i];
-  }
-  if (t < 16) {
-    float q = P[P_MHA_IN_B + t], v = P[P_MHA_IN_B + 32 + t];
+    sW[S_QC + t] = q; sW[S_KC + t] = k; sW[S_VC + t] = v;
+    const int tr = c * 16 + o;
+    sW[S_QCT + tr] = q; sW[S_KCT + tr] = k; sW[S_VCT + tr] = v;
+  } else if (t < 272) {
+    const int r = t - 256;
+    float q = tmp[1568 + r], v = tmp[1584 + r];
+#pragma unroll
     for (int m = 0; m < 16; ++m) {
-      q = fmaf(P[P_MHA_IN_W + t * 16 + m], P[P_ATT_Q_B + m], q);
-      v = fmaf(P[P_MHA_IN_W + (32 + t) * 16 + m], P[P_ATT_V_B + m], v);
+      q = fmaf(tmp[r * 16 + m], tmp[1536 + m], q);
+      v = fmaf(tmp[(32 + r) * 16 + m], tmp[1552 + m], v);
     }
-    sW[S_QBC + t] = q;
-    sW[S_VBC + t] = v;
-  }
-  for (int i = t; i < 2048; i += NT) sW[S_LUW0 + i] = P[P_LU_W0 + i];
-  for (int i = t; i < 512; i += NT) {
-    const float w = P[P_RD_W0 + i];
-    sW[S_RDW0 + i] = w;
-    sW[S_RDW0T + (i & 15) * 32 + (i >> 4)] = w;
-  }
-  if (t < 32) {
-    sW[S_LUB0 + t] = P[P_LU_B0 + t];
-    sW[S_LUW1 + t] = P[P_LU_W1 + t];
-    sW[S_RDB0 + t] = P[P_RD_B0 + t];
-    sW[S_RDW1 + t] = P[P_RD_W1 + t];
+    sW[S_QBC + r] = q;
+    sW[S_VBC + r] = v;
   }
 }
 
@@ -1612,7 +1622,7 @@ __global__ void __launch_bounds__(NT, 1) k_sgnn(const __grid_constant__ StepArgs
   float* gp = nullptr;
   if constexpr (TRAIN) {
     gp = a.gpart + (size_t)blockIdx.x * G_ROW;
-    for (int i = threadIdx.x; i < G_ROW; i += NT) gp[i] = 0.f;
+    for (int i = threadIdx.x; i < G_ROW / 4; i += NT) reinterpret_cast<float4*>(gp)[i] = f4(0.f);
   }
   __syncthreads();
   if (a.stamps && threadIdx.x == 0 && blockIdx.x < 160) a.stamps[64 + 160 + blockIdx.x] = clock64() - t_cta0;   // launch prologue
