@@ -229,9 +229,11 @@ def main():
     setup_s = time.time() - t0
 
     def step(i):
+        if world == 1:      # gradient + cross-CTA reduction + Adam in one launch
+            eng.ppo_step(blob, params, act, adv, ret, fixed, exps, 1.0 / gB, 1.0 / gI, ids=mb_ids[i % args.pool], out=grad)
+            return
         eng.ppo_grad(blob, params, act, adv, ret, fixed, exps, 1.0 / gB, 1.0 / gI, ids=mb_ids[i % args.pool], out=grad)
-        if world > 1:
-            dist.all_reduce(grad, op=dist.ReduceOp.SUM)
+        dist.all_reduce(grad, op=dist.ReduceOp.SUM)
         eng.apply(params, grad)
 
     def barrier():
@@ -316,10 +318,12 @@ def main():
             b.to(dev, out=dev_buf)
             dev_side.copy_(side_bufs[i & 1], non_blocking=True)      # actions | adv | ret | old log-probs | exps: one copy
             d = [dev_side[:BATCH * 2]] + [dev_side[BATCH * (2 + j):BATCH * (3 + j)] for j in range(4)]
-            eng.ppo_grad(b, params, d[0], d[1], d[2], d[3], d[4], 1.0 / gB, 1.0 / gI, out=grad)
-            if world > 1:
+            if world == 1:
+                eng.ppo_step(b, params, d[0], d[1], d[2], d[3], d[4], 1.0 / gB, 1.0 / gI, out=grad)
+            else:
+                eng.ppo_grad(b, params, d[0], d[1], d[2], d[3], d[4], 1.0 / gB, 1.0 / gI, out=grad)
                 dist.all_reduce(grad, op=dist.ReduceOp.SUM)
-            eng.apply(params, grad)
+                eng.apply(params, grad)
             pending[i + 1] = pool_ex.submit(pack_job, i + 1)          # overlaps with the GPU work just queued
             eng.read_losses(grad)                                     # D2H of the step's result (synchronises)
             h2d = b.nbytes + 4 * (BATCH * 2 + BATCH * 4)

@@ -176,6 +176,18 @@ struct StepArgs {
   float* scratch;      // [gridDim.x][scratch_stride]
   size_t scratch_stride;
   int n_cap, e_cap;
+  // fused tail (single GPU, no clipping this step): cross-CTA gradient reduction + attention chain + Adam inside
+  // the same launch, separated by grid barriers (cooperative launch: all CTAs are co-resident)
+  int fuse_tail;
+  float* params_rw;            // == params, writable
+  float* gsum;                 // [G_ROW]
+  float* grad_out;             // [UPB_GRAD_STRIDE]
+  float* adam_m;
+  float* adam_v;
+  const long long* steps_in;   // [4]
+  long long* steps_out;        // [4]
+  unsigned int* gridbar;       // [2] arrival counters, zero between launches
+  float lr, beta1, beta2, adam_eps;
   long long* stamps;   // optional [384]: [0,64) clock64() phase stamps, [64,224) busy cycles per CTA, [224,384) prologue cycles; of the first graph of CTA 0 (tools/phase_times.py)
 };
 
@@ -1614,6 +1626,153 @@ __device__ void graph_body(const StepArgs& a, const BlobHeader& hd, const GraphD
   UPB_STAMP(21);
 }
 
+
+// ---- fused tail: gradient reduction, attention chain, Adam (see upb_ppo_step) ------------------------------------------
+__device__ __forceinline__ void grid_arrive(unsigned int* ctr) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(ctr, 1u);
+  }
+}
+__device__ __forceinline__ void grid_wait(unsigned int* ctr, unsigned int target) {
+  if (threadIdx.x == 0) {
+    unsigned int v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr));
+    } while (v < target);
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+// torch.optim.Adam on one element with torch's operation order (same arithmetic as k_apply; no clipping here)
+__device__ __forceinline__ void adam_elem(const StepArgs& a, int i, float g, float step_size, float bc2_sqrt) {
+  const float w1 = 1.f - a.beta1, w2 = 1.f - a.beta2;
+  float m = a.adam_m[i], v = a.adam_v[i];
+  m = __fadd_rn(m, __fmul_rn(w1, __fsub_rn(g, m)));
+  v = __fadd_rn(__fmul_rn(v, a.beta2), __fmul_rn(__fmul_rn(w2, g), g));
+  const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(v), bc2_sqrt), a.adam_eps);
+  a.params_rw[i] = __fadd_rn(a.params_rw[i], __fmul_rn(-step_size, __fdiv_rn(m, denom)));
+  a.adam_m[i] = m;
+  a.adam_v[i] = v;
+}
+
+__device__ void fused_tail(const StepArgs& a, float* smem) {
+  constexpr int COLS = 128;                         // columns per CTA, 4 threads per column
+  const int tid = threadIdx.x;
+  const int nparts = gridDim.x;
+  __shared__ float sh_adam[8];
+  grid_arrive(a.gridbar);                           // all graphs of all CTAs are done, gpart rows are complete
+  grid_wait(a.gridbar, gridDim.x);
+  // per-segment Adam constants (encoder+value | land-use head | road head); a head whose stage is absent is skipped
+  if (tid < 32) {                                   // stage counts: does any graph of the minibatch use each head?
+    float s5 = 0.f, s6 = 0.f;
+    for (int c = tid; c < nparts; c += 32) {
+      s5 += __ldcg(a.gpart + (size_t)c * G_ROW + G_STATS + 5);
+      s6 += __ldcg(a.gpart + (size_t)c * G_ROW + G_STATS + 6);
+    }
+    s5 = warp_sum(s5); s6 = warp_sum(s6);
+    if (tid == 0) { sh_adam[6] = s5; sh_adam[7] = s6; }
+  }
+  __syncthreads();
+  const bool live_lu = sh_adam[6] > 0.f, live_rd = sh_adam[7] > 0.f;
+  if (tid < 3) {
+    const bool live = tid == 0 ? true : (tid == 1 ? live_lu : live_rd);
+    const long long stp = a.steps_in[1 + tid] + (live ? 1 : 0);
+    const double bc1 = 1.0 - pow((double)a.beta1, (double)(stp > 0 ? stp : 1));
+    const double bc2 = 1.0 - pow((double)a.beta2, (double)(stp > 0 ? stp : 1));
+    sh_adam[tid * 2 + 0] = (float)((double)a.lr / bc1);
+    sh_adam[tid * 2 + 1] = (float)sqrt(bc2);
+    if (blockIdx.x == 0) a.steps_out[1 + tid] = stp;
+  }
+  if (blockIdx.x == 0 && tid == 3) a.steps_out[0] = a.steps_in[0] + 1;
+  __syncthreads();
+  for (int c0 = blockIdx.x * COLS; c0 < G_ROW; c0 += gridDim.x * COLS) {
+    const int col = c0 + (tid >> 2), part = tid & 3;
+    float s = 0.f;
+    if (col < G_ROW)
+      for (int r = part; r < nparts; r += 4) s += __ldcg(a.gpart + (size_t)r * G_ROW + col);
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    if (part == 0 && col < G_ROW) {
+      a.gsum[col] = s;
+      const bool attn = (col >= P_MHA_IN_W && col < P_MHA_OUT_W) || (col >= P_ATT_Q_W && col < P_LU_W0);
+      if (col < NUM_PARAMS && !attn) {
+        a.grad_out[col] = s;
+        int seg = 0;
+        bool live = true;
+        if (col >= P_LU_W0 && col < P_RD_W0) { seg = 1; live = live_lu; }
+        else if (col >= P_RD_W0 && col < POLICY_END) { seg = 2; live = live_rd; }
+        if (live) adam_elem(a, col, s, sh_adam[seg * 2], sh_adam[seg * 2 + 1]);
+      } else if (col >= NUM_PARAMS && col < UPB_STAT_OFFSET) {
+        a.grad_out[col] = 0.f;
+      }
+      if (col >= G_STATS && col < G_STATS + 8) a.grad_out[UPB_STAT_OFFSET + (col - G_STATS)] = s;
+      if (col >= G_STATS + 8 && col < G_STATS + UPB_STAT_COUNT) a.grad_out[UPB_STAT_OFFSET + (col - G_STATS)] = 0.f;
+    }
+  }
+  grid_arrive(a.gridbar + 1);                       // this CTA's columns of gsum are written
+  if (blockIdx.x != 0) return;
+  grid_wait(a.gridbar + 1, gridDim.x);
+  // CTA 0: chain the composed-projection gradients to the six attention tensors (old parameter values!), then their Adam
+  float* sG = smem;                 // Qc | qbc | Kc | Vc | vbc gradients [816]
+  float* sWin = sG + 816;           // in_proj_weight [768]
+  float* sW3 = sWin + 768;          // Wq | Wk | Wv [768]
+  float* sB = sW3 + 768;            // bq | bk | bv [48]
+  float* sOut = sB + 48;            // new gradients: Wq,Wk,Wv [768] | Win [768] | bq,bk,bv [48] | bin [48]
+  const float* P = a.params_rw;
+  for (int i = tid; i < 816; i += NT) sG[i] = __ldcg(a.gsum + G_QC + i);
+  for (int i = tid; i < 768; i += NT) sWin[i] = P[P_MHA_IN_W + i];
+  if (tid < 256) { sW3[tid] = P[P_ATT_Q_W + tid]; sW3[256 + tid] = P[P_ATT_K_W + tid]; sW3[512 + tid] = P[P_ATT_V_W + tid]; }
+  if (tid < 16) { sB[tid] = P[P_ATT_Q_B + tid]; sB[16 + tid] = P[P_ATT_K_B + tid]; sB[32 + tid] = P[P_ATT_V_B + tid]; }
+  __syncthreads();
+  if (tid < 256) {
+    const int r = tid >> 4, c = tid & 15;
+    const int gC[3] = {0, 272, 528};
+    const int gB[3] = {256, -1, 784};
+#pragma unroll
+    for (int s3 = 0; s3 < 3; ++s3) {
+      const float* Win = sWin + s3 * 256;
+      const float* gc = sG + gC[s3];
+      const float* W = sW3 + s3 * 256;
+      float ga = 0.f, gb = 0.f;
+#pragma unroll
+      for (int rr = 0; rr < 16; ++rr) {
+        ga = fmaf(Win[rr * 16 + r], gc[rr * 16 + c], ga);
+        gb = fmaf(gc[r * 16 + rr], W[c * 16 + rr], gb);
+      }
+      if (gB[s3] >= 0) gb = fmaf(sG[gB[s3] + r], sB[s3 * 16 + c], gb);
+      sOut[s3 * 256 + tid] = ga;
+      sOut[768 + s3 * 256 + tid] = gb;
+      if (tid < 16) {
+        float b1 = 0.f, b2 = 0.f;
+        if (gB[s3] >= 0) {
+          for (int rr = 0; rr < 16; ++rr) b1 = fmaf(Win[rr * 16 + tid], sG[gB[s3] + rr], b1);
+          b2 = sG[gB[s3] + tid];
+        }
+        sOut[1536 + s3 * 16 + tid] = b1;
+        sOut[1584 + s3 * 16 + tid] = b2;
+      }
+    }
+  }
+  __syncthreads();
+  const int pW[3] = {P_ATT_Q_W, P_ATT_K_W, P_ATT_V_W};
+  const int pB[3] = {P_ATT_Q_B, P_ATT_K_B, P_ATT_V_B};
+  for (int i = tid; i < 1632; i += NT) {
+    int dst;
+    if (i < 768) dst = pW[i >> 8] + (i & 255);
+    else if (i < 1536) dst = P_MHA_IN_W + (i - 768);
+    else if (i < 1584) dst = pB[(i - 1536) >> 4] + ((i - 1536) & 15);
+    else dst = P_MHA_IN_B + (i - 1584);
+    const float g = sOut[i];
+    a.grad_out[dst] = g;
+    adam_elem(a, dst, g, sh_adam[0], sh_adam[1]);
+  }
+  __syncthreads();
+  if (tid == 0) { a.gridbar[0] = 0u; a.gridbar[1] = 0u; }      // every CTA has passed both barriers: ready for the next launch
+}
+
 template <bool TRAIN>
 __global__ void __launch_bounds__(NT, 1) k_sgnn(const __grid_constant__ StepArgs a) {
   extern __shared__ __align__(16) float smem[];
@@ -1662,6 +1821,9 @@ __global__ void __launch_bounds__(NT, 1) k_sgnn(const __grid_constant__ StepArgs
     __syncthreads();
   }
   if (a.stamps && threadIdx.x == 0 && blockIdx.x < 160) a.stamps[64 + blockIdx.x] = clock64() - t_cta0;           // CTA busy time
+  if constexpr (TRAIN) {
+    if (a.fuse_tail) fused_tail(a, smem);
+  }
 }
 
 }  // namespace upb

@@ -30,6 +30,9 @@ struct upb_ctx {
   long long* steps = nullptr;   // device [2][4] ping-pong step counters
   int steps_cur = 0;
   unsigned int* ticket = nullptr;
+  unsigned int* gridbar = nullptr;   // [2] grid-barrier counters of the fused tail
+  int64_t host_steps = 0;            // optimiser steps applied so far (mirrors the device counter)
+  int coop = 0;                      // cooperative launch supported
   float* host_pinned = nullptr; // [UPB_STAT_COUNT] pinned staging for upb_read_losses
   int64_t launches = 0;
   bool profiling = false;
@@ -161,6 +164,9 @@ extern "C" int upb_create(const upb_config* cfg, upb_ctx** out) {
   UPB_CUDA_F(cudaMalloc(&ctx->steps, sizeof(long long) * 8));
   UPB_CUDA_F(cudaMalloc(&ctx->ticket, sizeof(unsigned int)));
   UPB_CUDA_F(cudaMemset(ctx->ticket, 0, sizeof(unsigned int)));
+  UPB_CUDA_F(cudaMalloc(&ctx->gridbar, 2 * sizeof(unsigned int)));
+  UPB_CUDA_F(cudaMemset(ctx->gridbar, 0, 2 * sizeof(unsigned int)));
+  UPB_CUDA_F(cudaDeviceGetAttribute(&ctx->coop, cudaDevAttrCooperativeLaunch, cfg->device));
   UPB_CUDA_F(cudaMemset(ctx->adam_m, 0, sizeof(float) * NUM_PARAMS));
   UPB_CUDA_F(cudaMemset(ctx->adam_v, 0, sizeof(float) * NUM_PARAMS));
   UPB_CUDA_F(cudaMemset(ctx->steps, 0, sizeof(long long) * 8));
@@ -183,6 +189,7 @@ extern "C" void upb_destroy(upb_ctx* ctx) {
   cudaFree(ctx->adam_v);
   cudaFree(ctx->steps);
   cudaFree(ctx->ticket);
+  cudaFree(ctx->gridbar);
   if (ctx->host_pinned) cudaFreeHost(ctx->host_pinned);
   for (auto& ev : ctx->prof_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
   delete ctx;
@@ -248,6 +255,7 @@ extern "C" int upb_apply(upb_ctx* ctx, float* params, const float* grad, void* s
   a.steps_in = ctx->steps + 4 * ctx->steps_cur;
   a.steps_out = ctx->steps + 4 * (1 - ctx->steps_cur);
   ctx->steps_cur = 1 - ctx->steps_cur;
+  ctx->host_steps += 1;
   a.lr = ctx->cfg.lr;
   a.beta1 = ctx->cfg.beta1;
   a.beta2 = ctx->cfg.beta2;
@@ -256,6 +264,53 @@ extern "C" int upb_apply(upb_ctx* ctx, float* params, const float* grad, void* s
   k_apply<<<AP_BLOCKS, AP_THREADS, 0, (cudaStream_t)stream>>>(a);
   ctx->launches += 1;
   UPB_CUDA(cudaGetLastError());
+  return UPB_OK;
+}
+
+extern "C" int upb_ppo_step(upb_ctx* ctx, const void* blob_dev, const int32_t* ids, int count, float* params,
+                            const float* actions, const float* advantages, const float* returns,
+                            const float* fixed_log_probs, const float* exps, float inv_batch, float inv_ind,
+                            float* grad_out, void* stream) {
+  if (int rc = check_ctx(ctx, "ppo_step")) return rc;
+  const bool clip_now = ctx->cfg.clip_mode == UPB_CLIP_ALWAYS ||
+                        (ctx->cfg.clip_mode == UPB_CLIP_REFERENCE && ctx->host_steps == 0);
+  if (clip_now || !ctx->coop || count <= 0) {      // clipping needs a grid-wide norm first: use the two-call path
+    int rc = upb_ppo_grad(ctx, blob_dev, ids, count, params, actions, advantages, returns, fixed_log_probs, exps,
+                          inv_batch, inv_ind, grad_out, stream);
+    if (rc != UPB_OK) return rc;
+    return upb_apply(ctx, params, grad_out, stream);
+  }
+  if (!blob_dev || !params || !actions || !advantages || !returns || !fixed_log_probs || !exps || !grad_out)
+    return set_error(UPB_ERR_ARG, "ppo_step: bad argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  StepArgs a = base_args(ctx, blob_dev, ids, count, params, actions);
+  a.adv = advantages;
+  a.ret = returns;
+  a.fixed_lp = fixed_log_probs;
+  a.exps = exps;
+  a.inv_batch = inv_batch;
+  a.inv_ind = inv_ind;
+  a.fuse_tail = 1;
+  a.params_rw = params;
+  a.gsum = ctx->gsum;
+  a.grad_out = grad_out;
+  a.adam_m = ctx->adam_m;
+  a.adam_v = ctx->adam_v;
+  a.steps_in = ctx->steps + 4 * ctx->steps_cur;
+  a.steps_out = ctx->steps + 4 * (1 - ctx->steps_cur);
+  a.gridbar = ctx->gridbar;
+  a.lr = ctx->cfg.lr;
+  a.beta1 = ctx->cfg.beta1;
+  a.beta2 = ctx->cfg.beta2;
+  a.adam_eps = ctx->cfg.adam_eps;
+  const int grid = count < ctx->grid ? count : ctx->grid;
+  void* kargs[] = {&a};
+  const bool prof = prof_begin(ctx, s);
+  UPB_CUDA(cudaLaunchCooperativeKernel((void*)k_sgnn<true>, dim3(grid), dim3(NT), kargs, SMEM_BYTES, s));
+  prof_end(ctx, s, prof);
+  ctx->launches += 1;
+  ctx->steps_cur = 1 - ctx->steps_cur;
+  ctx->host_steps += 1;
   return UPB_OK;
 }
 
@@ -304,8 +359,10 @@ extern "C" int upb_set_opt_state(upb_ctx* ctx, const float* m_host, const float*
   UPB_CUDA(cudaDeviceSynchronize());
   if (m_host) UPB_CUDA(cudaMemcpy(ctx->adam_m, m_host, sizeof(float) * NUM_PARAMS, cudaMemcpyHostToDevice));
   if (v_host) UPB_CUDA(cudaMemcpy(ctx->adam_v, v_host, sizeof(float) * NUM_PARAMS, cudaMemcpyHostToDevice));
-  if (steps4_host)
+  if (steps4_host) {
     UPB_CUDA(cudaMemcpy(ctx->steps + 4 * ctx->steps_cur, steps4_host, sizeof(long long) * 4, cudaMemcpyHostToDevice));
+    ctx->host_steps = steps4_host[0];
+  }
   return UPB_OK;
 }
 

@@ -104,6 +104,24 @@ class Engine:
             "upb_ppo_grad")
         return out
 
+    def ppo_step(self, blob: PackedGraphs, params: torch.Tensor, actions: torch.Tensor, advantages: torch.Tensor,
+                 returns: torch.Tensor, fixed_log_probs: torch.Tensor, exps: torch.Tensor, inv_batch: float,
+                 inv_ind: float, ids: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None
+                 ) -> torch.Tensor:
+        """Single-GPU optimiser step in one launch (gradient + reduction + Adam, upb_ppo_step); falls back to
+        ppo_grad + apply inside the library on steps that clip.  Returns the gradient / statistics buffer."""
+        self._check_blob(blob)
+        dev = self.device
+        if out is None:
+            out = self.new_grad_buffer()
+        cnt = blob.count if ids is None else int(ids.numel())
+        _lib.check(_lib.lib().upb_ppo_step(
+            self._ctx, blob.dev_ptr(), _ptr(ids), cnt, params.data_ptr(), _f32(actions, dev).data_ptr(),
+            _f32(advantages, dev).data_ptr(), _f32(returns, dev).data_ptr(), _f32(fixed_log_probs, dev).data_ptr(),
+            _f32(exps, dev).data_ptr(), float(inv_batch), float(inv_ind), out.data_ptr(), self._stream()),
+            "upb_ppo_step")
+        return out
+
     def apply(self, params: torch.Tensor, grad: torch.Tensor) -> None:
         _lib.check(_lib.lib().upb_apply(self._ctx, params.data_ptr(), grad.data_ptr(), self._stream()), "upb_apply")
 

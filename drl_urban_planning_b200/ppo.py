@@ -92,11 +92,14 @@ class PPOUpdater:
     def minibatch_step(self, ids: torch.Tensor, global_batch: int, global_ind: int):
         """One optimiser step on the graphs `ids` (this rank's shard of a global minibatch of `global_batch`
         graphs, `global_ind` of which have exps != 0): urban_planning_agent.py:322-337."""
-        self.engine.ppo_grad(self.blob, self.params, self.actions, self.advantages, self.returns,
-                             self.fixed_log_probs, self.exps, 1.0 / max(global_batch, 1), 1.0 / max(global_ind, 1),
-                             ids=ids, out=self.grad)
-        self.allreduce(self.grad)
-        self.engine.apply(self.params, self.grad)
+        args = (self.blob, self.params, self.actions, self.advantages, self.returns, self.fixed_log_probs, self.exps,
+                1.0 / max(global_batch, 1), 1.0 / max(global_ind, 1))
+        if self.world == 1:
+            self.engine.ppo_step(*args, ids=ids, out=self.grad)          # one launch: gradient, reduction, Adam
+        else:
+            self.engine.ppo_grad(*args, ids=ids, out=self.grad)
+            self.allreduce(self.grad)
+            self.engine.apply(self.params, self.grad)
 
     # ------------------------------------------------------------------ the reference's update_params
     def update_params(self, states: Sequence, actions, rewards, masks, exps=None,

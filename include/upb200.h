@@ -126,6 +126,16 @@ int upb_ppo_grad(upb_ctx* ctx, const void* blob_dev, const int32_t* ids, int cou
  * stage count in the statistics is zero is skipped, as torch does for grad None. */
 int upb_apply(upb_ctx* ctx, float* params, const float* grad, void* stream);
 
+/* upb_ppo_grad + upb_apply in ONE launch for the single-GPU case (urban_planning_agent.py:330-337): when the step does
+ * not clip (every step but the first in UPB_CLIP_REFERENCE mode) the fused kernel ends with grid barriers, the
+ * cross-CTA gradient reduction, the attention chain rule and Adam; otherwise it falls back to the two calls above.
+ * grad_out still receives the gradient + statistics buffer.  Multi-GPU callers keep upb_ppo_grad / all-reduce /
+ * upb_apply. */
+int upb_ppo_step(upb_ctx* ctx, const void* blob_dev, const int32_t* ids, int count, float* params,
+                 const float* actions, const float* advantages, const float* returns,
+                 const float* fixed_log_probs, const float* exps, float inv_batch, float inv_ind,
+                 float* grad_out, void* stream);
+
 /* the 4 scalars the reference logs per minibatch (urban_planning_agent.py:338-345), from a gradient buffer:
  * out4 = {loss, value_loss, surr_loss, entropy_loss}.  Synchronises `stream`. */
 int upb_read_losses(upb_ctx* ctx, const float* grad, float* out4_host, void* stream);

@@ -304,3 +304,34 @@ def test_full_size_minibatch_properties(dev):
     assert rel(v.cpu().numpy()[sel], ref["value"]) < TOL
     assert rel(lp.cpu().numpy()[sel], ref["log_prob"]) < TOL
     assert rel(en.cpu().numpy()[sel], ref["entropy"]) < TOL
+
+
+def test_fused_step_matches_two_call_path(dev):
+    """upb_ppo_step (gradient + in-kernel reduction + Adam, one cooperative launch) against upb_ppo_grad + upb_apply:
+    same parameter trajectory and loss statistics over several steps, including the first (clipping) step that takes
+    the two-call path internally, mixed stages, and a head that never fires."""
+    for stages in (None, "land_use_only"):
+        count = 64
+        st = [0] * count if stages else None
+        states, actions = synth.make_states(51, "small", count, stages=st)
+        adv, ret, exps = synth.make_ppo_targets(51, count)
+        exps[3] = 0.0
+        flat = PL.default_init(51)
+        fixed = np.full((count, 1), -3.2, np.float32)
+        blob = pack_states(states).to(dev)
+        a = (t(actions, dev), t(adv, dev), t(ret, dev), t(fixed, dev), t(exps, dev))
+        n_ind = int((exps != 0).sum())
+        e1, e2 = make_engine(dev, blob.n_cap, blob.e_cap), make_engine(dev, blob.n_cap, blob.e_cap)
+        p1, p2 = t(flat, dev).clone(), t(flat, dev).clone()
+        for k in range(4):
+            g1 = e1.ppo_grad(blob, p1, *a, 1.0 / count, 1.0 / n_ind)
+            e1.apply(p1, g1)
+            g2 = e2.ppo_step(blob, p2, *a, 1.0 / count, 1.0 / n_ind)
+            torch.cuda.synchronize()
+            worst, where = per_tensor_rel(g2.cpu().numpy()[:PL.NUM_PARAMS], g1.cpu().numpy()[:PL.NUM_PARAMS])
+            assert worst < 1e-5, (k, worst, where)
+            assert np.allclose(e2.read_losses(g2), e1.read_losses(g1), rtol=1e-5, atol=1e-6)
+            assert rel(p2.cpu().numpy(), p1.cpu().numpy()) < 1e-6, k
+        assert e1.get_opt_state()[2].tolist() == e2.get_opt_state()[2].tolist()
+        m1, v1, _ = e1.get_opt_state(); m2, v2, _ = e2.get_opt_state()
+        assert rel(m2, m1) < 1e-5 and rel(v2, v1) < 1e-5
