@@ -60,4 +60,19 @@ constexpr int G_VBC = G_VC + 256;      // [16]      d/d(Win_v bv + bin_v)
 constexpr int G_STATS = G_VBC + 16;    // 14544: [8] statistics (see upb200.h)
 constexpr int G_ROW = 14592;           // row stride (multiple of 64)
 
+// beta^n for an integer step count by repeated squaring in double (a handful of multiplies; libdevice pow(double) costs
+// thousands of cycles in a one-thread critical path)
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+inline double ipow(double b, long long n) {
+  double r = 1.0;
+  while (n > 0) {
+    if (n & 1) r *= b;
+    b *= b;
+    n >>= 1;
+  }
+  return r;
+}
+
 }  // namespace upb

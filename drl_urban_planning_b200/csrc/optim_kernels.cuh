@@ -154,8 +154,8 @@ __global__ void __launch_bounds__(AP_THREADS) k_apply(const ApplyArgs a) {
     // per-segment Adam step counts: a head whose stage is absent has grad None and is skipped entirely
     const bool live = t == 0 ? true : (t == 1 ? live_lu : live_rd);
     const long long stp = a.steps_in[1 + t] + (live ? 1 : 0);
-    const double bc1 = 1.0 - pow((double)a.beta1, (double)(stp > 0 ? stp : 1));
-    const double bc2 = 1.0 - pow((double)a.beta2, (double)(stp > 0 ? stp : 1));
+    const double bc1 = 1.0 - ipow((double)a.beta1, stp > 0 ? stp : 1);
+    const double bc2 = 1.0 - ipow((double)a.beta2, stp > 0 ? stp : 1);
     sh[t * 2 + 0] = (float)((double)a.lr / bc1);
     sh[t * 2 + 1] = (float)sqrt(bc2);
     if (blockIdx.x == 0) a.steps_out[1 + t] = stp;

@@ -186,7 +186,7 @@ struct StepArgs {
   float* adam_v;
   const long long* steps_in;   // [4]
   long long* steps_out;        // [4]
-  unsigned int* gridbar;       // [2] arrival counters, zero between launches
+  unsigned int* gridbar;       // [3] two arrival counters + stage bits, zero between launches
   float lr, beta1, beta2, adam_eps;
   long long* stamps;   // optional [384]: [0,64) clock64() phase stamps, [64,224) busy cycles per CTA, [224,384) prologue cycles; of the first graph of CTA 0 (tools/phase_times.py)
 };
@@ -1646,53 +1646,99 @@ __device__ __forceinline__ void grid_wait(unsigned int* ctr, unsigned int target
   __syncthreads();
 }
 
-// torch.optim.Adam on one element with torch's operation order (same arithmetic as k_apply; no clipping here)
-__device__ __forceinline__ void adam_elem(const StepArgs& a, int i, float g, float step_size, float bc2_sqrt) {
+// torch.optim.Adam on one element with torch's operation order (same arithmetic as k_apply; no clipping here).
+// m, v, p are the element's current moments / value (loaded early by the caller so the latency overlaps).
+__device__ __forceinline__ void adam_elem(const StepArgs& a, int i, float g, float m, float v, float p, float step_size,
+                                          float bc2_sqrt) {
   const float w1 = 1.f - a.beta1, w2 = 1.f - a.beta2;
-  float m = a.adam_m[i], v = a.adam_v[i];
   m = __fadd_rn(m, __fmul_rn(w1, __fsub_rn(g, m)));
   v = __fadd_rn(__fmul_rn(v, a.beta2), __fmul_rn(__fmul_rn(w2, g), g));
   const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(v), bc2_sqrt), a.adam_eps);
-  a.params_rw[i] = __fadd_rn(a.params_rw[i], __fmul_rn(-step_size, __fdiv_rn(m, denom)));
+  a.params_rw[i] = __fadd_rn(p, __fmul_rn(-step_size, __fdiv_rn(m, denom)));
   a.adam_m[i] = m;
   a.adam_v[i] = v;
 }
 
-__device__ void fused_tail(const StepArgs& a, float* smem) {
-  constexpr int COLS = 128;                         // columns per CTA, 4 threads per column
+// Everything that does not depend on other CTAs' results is fetched or computed BEFORE the barrier it would otherwise
+// follow, so the serial part after each barrier is short.
+__device__ void fused_tail(const StepArgs& a, float* smem, unsigned stage_bits) {
+  constexpr int COLS = 128;                         // columns per CTA and pass, 4 threads per column
   const int tid = threadIdx.x;
   const int nparts = gridDim.x;
-  __shared__ float sh_adam[8];
-  grid_arrive(a.gridbar);                           // all graphs of all CTAs are done, gpart rows are complete
-  grid_wait(a.gridbar, gridDim.x);
-  // per-segment Adam constants (encoder+value | land-use head | road head); a head whose stage is absent is skipped
-  if (tid < 32) {                                   // stage counts: does any graph of the minibatch use each head?
-    float s5 = 0.f, s6 = 0.f;
-    for (int c = tid; c < nparts; c += 32) {
-      s5 += __ldcg(a.gpart + (size_t)c * G_ROW + G_STATS + 5);
-      s6 += __ldcg(a.gpart + (size_t)c * G_ROW + G_STATS + 6);
-    }
-    s5 = warp_sum(s5); s6 = warp_sum(s6);
-    if (tid == 0) { sh_adam[6] = s5; sh_adam[7] = s6; }
-  }
-  __syncthreads();
-  const bool live_lu = sh_adam[6] > 0.f, live_rd = sh_adam[7] > 0.f;
-  if (tid < 3) {
-    const bool live = tid == 0 ? true : (tid == 1 ? live_lu : live_rd);
-    const long long stp = a.steps_in[1 + tid] + (live ? 1 : 0);
-    const double bc1 = 1.0 - pow((double)a.beta1, (double)(stp > 0 ? stp : 1));
-    const double bc2 = 1.0 - pow((double)a.beta2, (double)(stp > 0 ? stp : 1));
+  __shared__ float sh_adam[12];                     // [seg][live ? 1 : 0][step_size, sqrt(bc2)]
+  __shared__ long long sh_steps[6];
+#define UPB_TSTAMP(ID) do { if (a.stamps != nullptr && blockIdx.x == 0 && threadIdx.x == 0) a.stamps[ID] = clock64(); } while (0)
+  UPB_TSTAMP(40);
+  if (tid == 0 && stage_bits) atomicOr(a.gridbar + 2, stage_bits);     // which policy heads this CTA's graphs used
+  if (tid < 6) {      // Adam bias corrections of the three segments, for "head live" and "head skipped"
+    const int seg = tid >> 1, live = tid & 1;
+    const long long stp = a.steps_in[1 + seg] + live;
+    const double bc1 = 1.0 - ipow((double)a.beta1, stp > 0 ? stp : 1);
+    const double bc2 = 1.0 - ipow((double)a.beta2, stp > 0 ? stp : 1);
     sh_adam[tid * 2 + 0] = (float)((double)a.lr / bc1);
     sh_adam[tid * 2 + 1] = (float)sqrt(bc2);
-    if (blockIdx.x == 0) a.steps_out[1 + tid] = stp;
+    sh_steps[tid] = stp;
   }
-  if (blockIdx.x == 0 && tid == 3) a.steps_out[0] = a.steps_in[0] + 1;
-  __syncthreads();
+  // this thread's column of the first pass: its moments / parameter do not depend on the reduction
+  const int col0 = blockIdx.x * COLS + (tid >> 2), part = tid & 3;
+  const bool attn0 = (col0 >= P_MHA_IN_W && col0 < P_MHA_OUT_W) || (col0 >= P_ATT_Q_W && col0 < P_LU_W0);
+  const bool real0 = part == 0 && col0 < NUM_PARAMS && !attn0;
+  float pm = 0.f, pv = 0.f, pp = 0.f;
+  if (real0) { pm = a.adam_m[col0]; pv = a.adam_v[col0]; pp = a.params_rw[col0]; }
+  // CTA 0 also prefetches what the attention chain needs from the (still old) parameters
+  float* sG = smem;                 // Qc | qbc | Kc | Vc | vbc gradients [816]
+  float* sWin = sG + 816;           // in_proj_weight [768]
+  float* sW3 = sWin + 768;          // Wq | Wk | Wv [768]
+  float* sB = sW3 + 768;            // bq | bk | bv [48]
+  float* sOut = sB + 48;            // new gradients: Wq,Wk,Wv [768] | Win [768] | bq,bk,bv [48] | bin [48]
+  const int pW[3] = {P_ATT_Q_W, P_ATT_K_W, P_ATT_V_W};
+  const int pB[3] = {P_ATT_Q_B, P_ATT_K_B, P_ATT_V_B};
+  float cm[4], cv[4], cp[4];
+  int cdst[4];
+  if (blockIdx.x == 0) {
+    const float* P = a.params_rw;
+    for (int i = tid; i < 768; i += NT) sWin[i] = P[P_MHA_IN_W + i];
+    if (tid < 256) { sW3[tid] = P[P_ATT_Q_W + tid]; sW3[256 + tid] = P[P_ATT_K_W + tid]; sW3[512 + tid] = P[P_ATT_V_W + tid]; }
+    if (tid < 16) { sB[tid] = P[P_ATT_Q_B + tid]; sB[16 + tid] = P[P_ATT_K_B + tid]; sB[32 + tid] = P[P_ATT_V_B + tid]; }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int i = tid + j * NT;
+      int dst = 0;
+      if (i < 768) dst = pW[i >> 8] + (i & 255);
+      else if (i < 1536) dst = P_MHA_IN_W + (i - 768);
+      else if (i < 1584) dst = pB[(i - 1536) >> 4] + ((i - 1536) & 15);
+      else if (i < 1632) dst = P_MHA_IN_B + (i - 1584);
+      cdst[j] = dst;
+      if (i < 1632) { cm[j] = a.adam_m[dst]; cv[j] = a.adam_v[dst]; cp[j] = P[dst]; }
+    }
+  }
+  grid_arrive(a.gridbar);                           // all graphs of all CTAs are done, gpart rows are complete
+  grid_wait(a.gridbar, gridDim.x);
+  UPB_TSTAMP(41);
+  unsigned bits;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(bits) : "l"(a.gridbar + 2));
+  const bool live_lu = bits & 1u, live_rd = bits & 2u;
+  if (blockIdx.x == 0 && tid < 4) {
+    // step counters: [0] global, [1] encoder+value, [2] land-use head, [3] road head
+    a.steps_out[tid] = tid == 0 ? a.steps_in[0] + 1
+                                : sh_steps[(tid - 1) * 2 + (tid == 1 ? 1 : (tid == 2 ? (live_lu ? 1 : 0) : (live_rd ? 1 : 0)))];
+  }
   for (int c0 = blockIdx.x * COLS; c0 < G_ROW; c0 += gridDim.x * COLS) {
-    const int col = c0 + (tid >> 2), part = tid & 3;
+    const int col = c0 + (tid >> 2);
     float s = 0.f;
-    if (col < G_ROW)
-      for (int r = part; r < nparts; r += 4) s += __ldcg(a.gpart + (size_t)r * G_ROW + col);
+    if (col < G_ROW) {      // rows part, part+4, ...: eight loads in flight per thread, fixed summation order
+      const float* src = a.gpart + col;
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, s4 = 0.f, s5 = 0.f, s6 = 0.f, s7 = 0.f;
+      int r = part;
+      for (; r + 28 < nparts; r += 32) {
+        s0 += __ldcg(src + (size_t)r * G_ROW);        s1 += __ldcg(src + (size_t)(r + 4) * G_ROW);
+        s2 += __ldcg(src + (size_t)(r + 8) * G_ROW);  s3 += __ldcg(src + (size_t)(r + 12) * G_ROW);
+        s4 += __ldcg(src + (size_t)(r + 16) * G_ROW); s5 += __ldcg(src + (size_t)(r + 20) * G_ROW);
+        s6 += __ldcg(src + (size_t)(r + 24) * G_ROW); s7 += __ldcg(src + (size_t)(r + 28) * G_ROW);
+      }
+      for (; r < nparts; r += 4) s0 += __ldcg(src + (size_t)r * G_ROW);
+      s = ((s0 + s1) + (s2 + s3)) + ((s4 + s5) + (s6 + s7));
+    }
     s += __shfl_xor_sync(0xffffffffu, s, 1);
     s += __shfl_xor_sync(0xffffffffu, s, 2);
     if (part == 0 && col < G_ROW) {
@@ -1704,7 +1750,10 @@ __device__ void fused_tail(const StepArgs& a, float* smem) {
         bool live = true;
         if (col >= P_LU_W0 && col < P_RD_W0) { seg = 1; live = live_lu; }
         else if (col >= P_RD_W0 && col < POLICY_END) { seg = 2; live = live_rd; }
-        if (live) adam_elem(a, col, s, sh_adam[seg * 2], sh_adam[seg * 2 + 1]);
+        if (live) {
+          if (col != col0) { pm = a.adam_m[col]; pv = a.adam_v[col]; pp = a.params_rw[col]; }     // later passes (small grids)
+          adam_elem(a, col, s, pm, pv, pp, sh_adam[(seg * 2 + 1) * 2], sh_adam[(seg * 2 + 1) * 2 + 1]);
+        }
       } else if (col >= NUM_PARAMS && col < UPB_STAT_OFFSET) {
         a.grad_out[col] = 0.f;
       }
@@ -1712,20 +1761,13 @@ __device__ void fused_tail(const StepArgs& a, float* smem) {
       if (col >= G_STATS + 8 && col < G_STATS + UPB_STAT_COUNT) a.grad_out[UPB_STAT_OFFSET + (col - G_STATS)] = 0.f;
     }
   }
+  UPB_TSTAMP(42);
   grid_arrive(a.gridbar + 1);                       // this CTA's columns of gsum are written
   if (blockIdx.x != 0) return;
   grid_wait(a.gridbar + 1, gridDim.x);
-  // CTA 0: chain the composed-projection gradients to the six attention tensors (old parameter values!), then their Adam
-  float* sG = smem;                 // Qc | qbc | Kc | Vc | vbc gradients [816]
-  float* sWin = sG + 816;           // in_proj_weight [768]
-  float* sW3 = sWin + 768;          // Wq | Wk | Wv [768]
-  float* sB = sW3 + 768;            // bq | bk | bv [48]
-  float* sOut = sB + 48;            // new gradients: Wq,Wk,Wv [768] | Win [768] | bq,bk,bv [48] | bin [48]
-  const float* P = a.params_rw;
+  UPB_TSTAMP(43);
+  // CTA 0: chain the composed-projection gradients to the six attention tensors (old parameter values), then their Adam
   for (int i = tid; i < 816; i += NT) sG[i] = __ldcg(a.gsum + G_QC + i);
-  for (int i = tid; i < 768; i += NT) sWin[i] = P[P_MHA_IN_W + i];
-  if (tid < 256) { sW3[tid] = P[P_ATT_Q_W + tid]; sW3[256 + tid] = P[P_ATT_K_W + tid]; sW3[512 + tid] = P[P_ATT_V_W + tid]; }
-  if (tid < 16) { sB[tid] = P[P_ATT_Q_B + tid]; sB[16 + tid] = P[P_ATT_K_B + tid]; sB[32 + tid] = P[P_ATT_V_B + tid]; }
   __syncthreads();
   if (tid < 256) {
     const int r = tid >> 4, c = tid & 15;
@@ -1757,20 +1799,18 @@ __device__ void fused_tail(const StepArgs& a, float* smem) {
     }
   }
   __syncthreads();
-  const int pW[3] = {P_ATT_Q_W, P_ATT_K_W, P_ATT_V_W};
-  const int pB[3] = {P_ATT_Q_B, P_ATT_K_B, P_ATT_V_B};
-  for (int i = tid; i < 1632; i += NT) {
-    int dst;
-    if (i < 768) dst = pW[i >> 8] + (i & 255);
-    else if (i < 1536) dst = P_MHA_IN_W + (i - 768);
-    else if (i < 1584) dst = pB[(i - 1536) >> 4] + ((i - 1536) & 15);
-    else dst = P_MHA_IN_B + (i - 1584);
-    const float g = sOut[i];
-    a.grad_out[dst] = g;
-    adam_elem(a, dst, g, sh_adam[0], sh_adam[1]);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {       // 1632 = 3.2 x 512 elements
+    const int i = tid + j * NT;
+    if (i < 1632) {
+      const float g = sOut[i];
+      a.grad_out[cdst[j]] = g;
+      adam_elem(a, cdst[j], g, cm[j], cv[j], cp[j], sh_adam[2], sh_adam[3]);     // segment 0 (encoder), live
+    }
   }
   __syncthreads();
-  if (tid == 0) { a.gridbar[0] = 0u; a.gridbar[1] = 0u; }      // every CTA has passed both barriers: ready for the next launch
+  if (tid == 0) { a.gridbar[0] = 0u; a.gridbar[1] = 0u; a.gridbar[2] = 0u; }   // all CTAs are past both barriers
+  UPB_TSTAMP(44);
 }
 
 template <bool TRAIN>
@@ -1788,9 +1828,11 @@ __global__ void __launch_bounds__(NT, 1) k_sgnn(const __grid_constant__ StepArgs
   const BlobHeader& hd = *reinterpret_cast<const BlobHeader*>(a.blob);
   const GraphDesc* descs = reinterpret_cast<const GraphDesc*>(a.blob + hd.off_desc);
   float* scr = a.scratch + (size_t)blockIdx.x * a.scratch_stride;
+  unsigned stage_bits = 0;     // bit 0: a land-use graph, bit 1: a road graph was walked by this CTA
   for (int item = blockIdx.x; item < a.count; item += gridDim.x) {
     const int gid = a.ids ? a.ids[item] : item;
     const GraphDesc d = descs[gid];
+    stage_bits |= 1u << (d.stage & 1);
     if (d.n > a.n_cap || d.e > a.e_cap || d.n < 1) {   // larger than the context was sized for: skip, flag
       if (threadIdx.x == 0) {
         if constexpr (TRAIN) gp[G_STATS + 7] += 1.f;
@@ -1822,7 +1864,7 @@ __global__ void __launch_bounds__(NT, 1) k_sgnn(const __grid_constant__ StepArgs
   }
   if (a.stamps && threadIdx.x == 0 && blockIdx.x < 160) a.stamps[64 + blockIdx.x] = clock64() - t_cta0;           // CTA busy time
   if constexpr (TRAIN) {
-    if (a.fuse_tail) fused_tail(a, smem);
+    if (a.fuse_tail) fused_tail(a, smem, stage_bits);
   }
 }
 

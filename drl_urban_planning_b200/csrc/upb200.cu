@@ -164,8 +164,8 @@ extern "C" int upb_create(const upb_config* cfg, upb_ctx** out) {
   UPB_CUDA_F(cudaMalloc(&ctx->steps, sizeof(long long) * 8));
   UPB_CUDA_F(cudaMalloc(&ctx->ticket, sizeof(unsigned int)));
   UPB_CUDA_F(cudaMemset(ctx->ticket, 0, sizeof(unsigned int)));
-  UPB_CUDA_F(cudaMalloc(&ctx->gridbar, 2 * sizeof(unsigned int)));
-  UPB_CUDA_F(cudaMemset(ctx->gridbar, 0, 2 * sizeof(unsigned int)));
+  UPB_CUDA_F(cudaMalloc(&ctx->gridbar, 4 * sizeof(unsigned int)));
+  UPB_CUDA_F(cudaMemset(ctx->gridbar, 0, 4 * sizeof(unsigned int)));
   UPB_CUDA_F(cudaDeviceGetAttribute(&ctx->coop, cudaDevAttrCooperativeLaunch, cfg->device));
   UPB_CUDA_F(cudaMemset(ctx->adam_m, 0, sizeof(float) * NUM_PARAMS));
   UPB_CUDA_F(cudaMemset(ctx->adam_v, 0, sizeof(float) * NUM_PARAMS));
