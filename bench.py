@@ -291,40 +291,63 @@ def main():
         host_fix = torch.full((BATCH,), -4.0).pin_memory()
         host_exp = torch.ones(BATCH).pin_memory()
         host_side = torch.cat([torch.zeros(BATCH * 2), host_adv, host_ret, host_fix, host_exp]).pin_memory()
-        dev_side = torch.empty_like(host_side, device=dev)
-        # Two pinned staging buffers (with headroom, so a refill never re-measures): while the GPU works on step i the
-        # host packer (C, releases the GIL) fills the buffer of step i+1.  Every step's blob and per-sample arrays still
-        # cross PCIe inside the timed region and every step ends with a D2H read of its losses.
+        # Three-stage pipeline, one step deep per stage: the host packer (C, releases the GIL, persistent worker pool)
+        # fills the pinned buffer of step i+2 while the copy stream uploads step i+1 and the GPU works on step i.
+        # Every step's blob and per-sample arrays still cross PCIe inside the timed region and every step ends with a
+        # D2H read of its losses.
         from concurrent.futures import ThreadPoolExecutor
         cap = int(blob.nbytes / args.pool * 1.3)
         host_bufs = [torch.empty(cap, dtype=torch.uint8).pin_memory() for _ in range(2)]
         side_bufs = [host_side.clone().pin_memory() for _ in range(2)]
-        dev_buf = torch.empty(cap, dtype=torch.uint8, device=dev)
+        dev_bufs = [torch.empty(cap, dtype=torch.uint8, device=dev) for _ in range(2)]
+        dev_sides = [torch.empty_like(host_side, device=dev) for _ in range(2)]
+        copy_stream = torch.cuda.Stream(device=dev)
+        ev_h2d = [torch.cuda.Event() for _ in range(2)]      # upload of the buffer pair finished
+        ev_done = [torch.cuda.Event() for _ in range(2)]     # the step that read the device buffers finished
+        for ev in ev_h2d + ev_done:
+            ev.record()
         n_e2e = max(3, min(args.steps, 20))
         h2d = 0
         pool_ex = ThreadPoolExecutor(1)
 
         def pack_job(i):
+            j = i & 1
+            ev_h2d[j].synchronize()                                  # the previous upload from this pinned buffer is over
             lo = (i % args.pool) * BATCH
-            b = pk(states[lo:lo + BATCH], blob.n_cap, blob.e_cap, out_host=host_bufs[i & 1])
-            side_bufs[i & 1][:BATCH * 2].copy_(torch.from_numpy(actions[lo:lo + BATCH].reshape(-1)))
+            b = pk(states[lo:lo + BATCH], blob.n_cap, blob.e_cap, out_host=host_bufs[j])
+            side_bufs[j][:BATCH * 2].copy_(torch.from_numpy(actions[lo:lo + BATCH].reshape(-1)))
+            return b
+
+        def upload(i):
+            j = i & 1
+            b = pending.pop(i).result()
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(ev_done[j])                   # step i-2 no longer reads these device buffers
+                b.to(dev, out=dev_bufs[j])
+                dev_sides[j].copy_(side_bufs[j], non_blocking=True)  # actions | adv | ret | old log-probs | exps: one copy
+                ev_h2d[j].record(copy_stream)
             return b
 
         pending = {0: pool_ex.submit(pack_job, 0)}
+        uploaded = {0: upload(0)}
+        pending[1] = pool_ex.submit(pack_job, 1)
 
         def e2e_step(i):
             nonlocal h2d
-            b = pending.pop(i).result()
-            b.to(dev, out=dev_buf)
-            dev_side.copy_(side_bufs[i & 1], non_blocking=True)      # actions | adv | ret | old log-probs | exps: one copy
-            d = [dev_side[:BATCH * 2]] + [dev_side[BATCH * (2 + j):BATCH * (3 + j)] for j in range(4)]
+            j = i & 1
+            uploaded[i + 1] = upload(i + 1)                           # H2D of the next step, on the copy stream
+            pending[i + 2] = pool_ex.submit(pack_job, i + 2)          # host packing two steps ahead
+            b = uploaded.pop(i)
+            side = dev_sides[j]
+            d = [side[:BATCH * 2]] + [side[BATCH * (2 + q):BATCH * (3 + q)] for q in range(4)]
+            torch.cuda.current_stream().wait_event(ev_h2d[j])
             if world == 1:
                 eng.ppo_step(b, params, d[0], d[1], d[2], d[3], d[4], 1.0 / gB, 1.0 / gI, out=grad)
             else:
                 eng.ppo_grad(b, params, d[0], d[1], d[2], d[3], d[4], 1.0 / gB, 1.0 / gI, out=grad)
                 dist.all_reduce(grad, op=dist.ReduceOp.SUM)
                 eng.apply(params, grad)
-            pending[i + 1] = pool_ex.submit(pack_job, i + 1)          # overlaps with the GPU work just queued
+            ev_done[j].record()
             eng.read_losses(grad)                                     # D2H of the step's result (synchronises)
             h2d = b.nbytes + 4 * (BATCH * 2 + BATCH * 4)
 
@@ -336,14 +359,16 @@ def main():
             e2e_step(2 + i)
         barrier()
         dt = torch.tensor([time.perf_counter() - t1], device=dev)
-        pending.popitem()[1].result()
+        for f in pending.values():
+            f.result()
+        torch.cuda.synchronize()
         pool_ex.shutdown()
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         e2e = {"value": BATCH * world * n_e2e / float(dt.item()), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": 32, "steps": n_e2e,
-               "path": "reference-layout host states -> upb_pack_fill -> pinned (double-buffered, packer thread overlaps the GPU) "
-                       "-> H2D -> upb_ppo_grad/upb_apply -> D2H losses"}
+               "path": "reference-layout host states -> upb_pack_fill -> pinned -> H2D (copy stream) -> upb_ppo_step -> D2H losses; "
+                       "packer, upload and step of consecutive minibatches overlap"}
 
     # ---- CPU baseline beside it (rank 0, N=1): oracle port of the reference's padded eager dataflow
     cpu = None

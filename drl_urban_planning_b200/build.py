@@ -42,7 +42,9 @@ def build_pyptr(force: bool = False) -> str:
     src = os.path.join(CSRC, "pyptr.c")
     if not force and os.path.exists(PYPTR) and os.path.getmtime(PYPTR) >= os.path.getmtime(src):
         return PYPTR
-    cmd = ["gcc", "-O2", "-shared", "-fPIC", "-I", sysconfig.get_paths()["include"], "-o", PYPTR, src]
+    import numpy
+    cmd = ["gcc", "-O2", "-shared", "-fPIC", "-I", sysconfig.get_paths()["include"], "-I", numpy.get_include(),
+           "-o", PYPTR, src]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("gcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)

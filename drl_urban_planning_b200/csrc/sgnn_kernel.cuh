@@ -207,6 +207,14 @@ __device__ __forceinline__ float exp2a(float a) {
   const float t = fminf(fmaxf(a * 2.8853900817779268f, -115.41560327111707f), 115.41560327111707f);
   return ex2_approx(t);
 }
+// 16-byte asynchronous global -> shared copies (LDGSTS): no register staging, every copy of a phase is in flight at once
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 __device__ __forceinline__ float4 f4(float a) { return make_float4(a, a, a, a); }
@@ -1094,6 +1102,13 @@ __device__ __forceinline__ void softmax_seeds(const StepArgs& a, const BlobHeade
     if (a.stamps != nullptr && blockIdx.x == 0 && threadIdx.x == 0 && first_item) a.stamps[ID] = clock64(); \
   } while (0)
 
+// probe: arrival time of every warp at one point of the graph body (moved around while tuning; tools/phase_times.py)
+#define UPB_WSTAMP()                                                                                         \
+  do {                                                                                                       \
+    if (a.stamps != nullptr && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && first_item)                      \
+      a.stamps[46 + (threadIdx.x >> 5)] = clock64();                                                         \
+  } while (0)
+
 template <bool TRAIN, bool BIG>
 __device__ void graph_body(const StepArgs& a, const BlobHeader& hd, const GraphDesc& d, int gid, float* smem,
                            float* gp, float* scr, bool first_item) {
@@ -1140,22 +1155,27 @@ __device__ void graph_body(const StepArgs& a, const BlobHeader& hd, const GraphD
     uint32_t* adj_s = reinterpret_cast<uint32_t*>(smem + S_ADJ);
     uint32_t* cuv_s = reinterpret_cast<uint32_t*>(smem + S_CUV);
     int* cidx_s = reinterpret_cast<int*>(smem + S_CIDX);
-    // stage the graph's neighbourhood lists in shared memory (16-byte vectors; blob sections are padded)
+    // stage the graph's neighbourhood lists and node features in shared memory (asynchronous 16-byte copies; blob
+    // sections are padded).  The features park in the EPQ region, which is idle until the first EPQ phase.
     {
       const uint4* s0 = reinterpret_cast<const uint4*>(rp_g);
       uint4* d0 = reinterpret_cast<uint4*>(rp_s);
-      for (int i = tid; i < (n + 1 + 7) / 8; i += NT) d0[i] = s0[i];
+      for (int i = tid; i < (n + 1 + 7) / 8; i += NT) cp_async16(d0 + i, s0 + i);
       const uint4* so = reinterpret_cast<const uint4*>(ord_g);
       uint4* dord = reinterpret_cast<uint4*>(smem + S_ORD);
-      for (int i = tid; i < d.ord_rounds * NW; i += NT) dord[i] = so[i];      // 8 node ids (16 bytes) per warp-task
+      for (int i = tid; i < d.ord_rounds * NW; i += NT) cp_async16(dord + i, so + i);   // 8 node ids per warp-task
       const uint4* s1 = reinterpret_cast<const uint4*>(adj_g);
       uint4* d1 = reinterpret_cast<uint4*>(adj_s);
-      for (int i = tid; i < (2 * e + 3) / 4; i += NT) d1[i] = s1[i];
+      for (int i = tid; i < (2 * e + 3) / 4; i += NT) cp_async16(d1 + i, s1 + i);
       const uint4* s2 = reinterpret_cast<const uint4*>(cuv_g);
       const uint4* s3 = reinterpret_cast<const uint4*>(cidx_g);
       uint4* d2 = reinterpret_cast<uint4*>(cuv_s);
       uint4* d3 = reinterpret_cast<uint4*>(cidx_s);
-      for (int i = tid; i < (k + 3) / 4; i += NT) { d2[i] = s2[i]; d3[i] = s3[i]; }
+      for (int i = tid; i < (k + 3) / 4; i += NT) { cp_async16(d2 + i, s2 + i); cp_async16(d3 + i, s3 + i); }
+      const float4* sx = reinterpret_cast<const float4*>(g.x);
+      float4* dx = reinterpret_cast<float4*>(smem + S_EPQ);
+      for (int i = tid; i < n * 6; i += NT) cp_async16(dx + i, sx + i);
+      cp_async_commit();
     }
     g.rp = rp_s; g.adj = adj_s; g.cuv = cuv_s; g.cidx = cidx_s;
     g.ord = reinterpret_cast<const uint16_t*>(smem + S_ORD);
@@ -1173,33 +1193,59 @@ __device__ void graph_body(const StepArgs& a, const BlobHeader& hd, const GraphD
     if (tid == 113) sc[SC_ADV] = a.adv[gid];
   }
   if (tid == 114) reinterpret_cast<int*>(sc)[SC_QUEUE] = 0;
+  if constexpr (!BIG) cp_async_wait_all();
   __syncthreads();
   UPB_STAMP(1);
 
   // ================================================================================ forward
   if (warp < 2) numeric_l0(vn, sV + V_X52, sV + V_A0, warp, lane);   // numeric encoder, layer 0 (state_encoder.py:35-57)
   for (int i = tid; i < n; i += NT) g.inv[i] = 1.0f / ((float)(g.rp[i + 1] - g.rp[i]) + EPS_DEG);
-  // h^0 = X We^T + be (state_encoder.py:189); 4 lanes per node, 4 channels per lane
-  for (int task = tid; task < n * 4; task += NT) {
-    const int i = task >> 2;
-    const float* xr = g.x + (size_t)i * FS;
-    float4 xv[6];
+  // h^0 = X We^T + be (state_encoder.py:189)
+  if constexpr (BIG) {   // 4 lanes per node, 4 channels per lane, features from global memory
+    for (int task = tid; task < n * 4; task += NT) {
+      const int i = task >> 2;
+      const float* xr = g.x + (size_t)i * FS;
+      float4 xv[6];
 #pragma unroll
-    for (int f4i = 0; f4i < 6; ++f4i) xv[f4i] = __ldg(reinterpret_cast<const float4*>(xr) + f4i);
-    float4 acc = ld4(sW + S_BE + q * 4);
+      for (int f4i = 0; f4i < 6; ++f4i) xv[f4i] = __ldg(reinterpret_cast<const float4*>(xr) + f4i);
+      float4 acc = ld4(sW + S_BE + q * 4);
 #pragma unroll
-    for (int f4i = 0; f4i < 6; ++f4i) {
+      for (int f4i = 0; f4i < 6; ++f4i) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float xs = comp(xv[f4i], j);
-        const float4 w = ld4(sW + S_WET + (f4i * 4 + j) * 16 + q * 4);
-        acc.x = fmaf(w.x, xs, acc.x); acc.y = fmaf(w.y, xs, acc.y);
-        acc.z = fmaf(w.z, xs, acc.z); acc.w = fmaf(w.w, xs, acc.w);
+        for (int j = 0; j < 4; ++j) {
+          const float xs = comp(xv[f4i], j);
+          const float4 w = ld4(sW + S_WET + (f4i * 4 + j) * 16 + q * 4);
+          acc.x = fmaf(w.x, xs, acc.x); acc.y = fmaf(w.y, xs, acc.y);
+          acc.z = fmaf(w.z, xs, acc.z); acc.w = fmaf(w.w, xs, acc.w);
+        }
       }
+      st4(g.H + i * 16 + q * 4, acc);
+      if (TRAIN) st4(g.H0g + i * 16 + q * 4, acc);
     }
-    st4(g.H + i * 16 + q * 4, acc);
-    if (TRAIN) st4(g.H0g + i * 16 + q * 4, acc);
+  } else {   // 8 lanes per node, 2 channels per lane: the lane's 24x2 weight slice stays in registers, features from
+             // the staged rows (4 consecutive nodes per warp load: conflict-free), packed FMAs
+    const int c2 = (lane & 7) * 2;
+    float2 w[24];
+#pragma unroll
+    for (int f = 0; f < 24; ++f) w[f] = *reinterpret_cast<const float2*>(sW + S_WET + f * 16 + c2);
+    const float2 be = *reinterpret_cast<const float2*>(sW + S_BE + c2);
+    const float* xs = smem + S_EPQ;
+    for (int i = warp * 4 + (lane >> 3); i < n; i += NW * 4) {
+      const float4* xr = reinterpret_cast<const float4*>(xs + i * FS);
+      float2 acc = be;
+#pragma unroll
+      for (int f4i = 0; f4i < 6; ++f4i) {
+        const float4 xv = xr[f4i];
+        acc = __ffma2_rn(w[f4i * 4 + 0], make_float2(xv.x, xv.x), acc);
+        acc = __ffma2_rn(w[f4i * 4 + 1], make_float2(xv.y, xv.y), acc);
+        acc = __ffma2_rn(w[f4i * 4 + 2], make_float2(xv.z, xv.z), acc);
+        acc = __ffma2_rn(w[f4i * 4 + 3], make_float2(xv.w, xv.w), acc);
+      }
+      *reinterpret_cast<float2*>(g.H + i * 16 + c2) = acc;
+      if (TRAIN) *reinterpret_cast<float2*>(g.H0g + i * 16 + c2) = acc;
+    }
   }
+  UPB_WSTAMP();
   if (warp == NW - 1 && lane < 16) {   // current node through the same encoder (state_encoder.py:190-191)
     float s = sW[S_BE + lane];
 #pragma unroll
@@ -1518,8 +1564,14 @@ __device__ void graph_body(const StepArgs& a, const BlobHeader& hd, const GraphD
     const float* hin = l == 0 ? g.H0g : g.H1g;     // layer input h^l (global scratch)
     int exact = exact_last;
     if (l == 0) {   // EPQ of layer 0 was overwritten by layer 1: reload the copy saved by the forward pass
+      if constexpr (BIG) {
 #pragma unroll 2
-      for (int i = tid; i < n * 8; i += NT) st4(g.EPQ + i * 4, __ldcg(reinterpret_cast<const float4*>(E0g) + i));
+        for (int i = tid; i < n * 8; i += NT) st4(g.EPQ + i * 4, __ldcg(reinterpret_cast<const float4*>(E0g) + i));
+      } else {   // same thread wrote the same elements in the forward pass
+        for (int i = tid; i < n * 8; i += NT) cp_async16(g.EPQ + i * 4, E0g + i * 4);
+        cp_async_commit();
+        cp_async_wait_all();
+      }
       exact = exact_first;
       __syncthreads();
       UPB_STAMP(17);
@@ -1539,17 +1591,20 @@ __device__ void graph_body(const StepArgs& a, const BlobHeader& hd, const GraphD
       for (int x = 0; x < 4; ++x)
 #pragma unroll
         for (int y = 0; y < 4; ++y) acc[x][y] = 0.f;
-      for (int i = warp; i < n; i += 4 * KW) {   // four nodes per trip: their global h rows are in flight together
-        float4 gq[4], hv[4];
+      for (int i = warp; i < n; i += 8 * KW) {   // eight nodes per trip: their global h rows are in flight together
+        float4 gq[8], hv[8];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < 8; ++u) {
           const int ii = i + u * KW;
-          const bool ok = ii < n;
-          hv[u] = ok ? __ldcg(reinterpret_cast<const float4*>(hin + (size_t)ii * 16 + tc * 4)) : f4(0.f);
-          gq[u] = ok ? ld4(g.GPQ + ii * 32 + to * 4) : f4(0.f);
+          hv[u] = ii < n ? __ldcg(reinterpret_cast<const float4*>(hin + (size_t)ii * 16 + tc * 4)) : f4(0.f);
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
+        for (int u = 0; u < 8; ++u) {
+          const int ii = i + u * KW;
+          gq[u] = ii < n ? ld4(g.GPQ + ii * 32 + to * 4) : f4(0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
 #pragma unroll
           for (int x = 0; x < 4; ++x) {
             const float gx = comp(gq[u], x);
@@ -1578,7 +1633,18 @@ __device__ void graph_body(const StepArgs& a, const BlobHeader& hd, const GraphD
 
   // ---- node encoder backward: g_We = g_h0^T X + g_hc x_cur^T, g_be = sum g_h0 + g_hc
   {
-    float* redbuf = smem + S_EPQ;                // [NW][384]
+    float* redbuf = smem + S_GPQ;                // [NW][384]  (GPQ is dead after the last g_h)
+    const float* xsrc = g.x;
+    if constexpr (!BIG) {                        // features back into the (dead) EPQ region, one asynchronous sweep
+      const float4* sx = reinterpret_cast<const float4*>(g.x);
+      float4* dx = reinterpret_cast<float4*>(smem + S_EPQ);
+      for (int i = tid; i < n * 6; i += NT) cp_async16(dx + i, sx + i);
+      cp_async_commit();
+      xsrc = smem + S_EPQ;
+    }
+    float4 hs = f4(0.f);
+    for (int task = tid; task < n * 4; task += NT) hs = hs + ld4(g.H + (task >> 2) * 16 + q * 4);
+    if constexpr (!BIG) { cp_async_wait_all(); __syncthreads(); }
     const int tcc = lane / 6, tf = lane % 6;     // 4 channel tiles x 6 feature tiles (lanes 24..31 idle)
     float acc[4][4];
 #pragma unroll
@@ -1586,13 +1652,14 @@ __device__ void graph_body(const StepArgs& a, const BlobHeader& hd, const GraphD
 #pragma unroll
       for (int y = 0; y < 4; ++y) acc[x][y] = 0.f;
     if (lane < 24) {
-      for (int i = warp; i < n; i += 4 * NW) {   // four nodes per trip: their global feature rows are in flight together
+      for (int i = warp; i < n; i += 4 * NW) {   // four nodes per trip
         float4 gh[4], xv[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const int ii = i + u * NW;
           const bool ok = ii < n;
-          xv[u] = ok ? __ldg(reinterpret_cast<const float4*>(g.x + (size_t)ii * FS) + tf) : f4(0.f);
+          if constexpr (BIG) xv[u] = ok ? __ldg(reinterpret_cast<const float4*>(xsrc + (size_t)ii * FS) + tf) : f4(0.f);
+          else xv[u] = ok ? ld4(xsrc + ii * FS + tf * 4) : f4(0.f);
           gh[u] = ok ? ld4(g.H + ii * 16 + tcc * 4) : f4(0.f);
         }
 #pragma unroll
@@ -1608,8 +1675,6 @@ __device__ void graph_body(const StepArgs& a, const BlobHeader& hd, const GraphD
       for (int x = 0; x < 4; ++x)
         st4(redbuf + warp * 384 + (tcc * 4 + x) * 24 + tf * 4, make_float4(acc[x][0], acc[x][1], acc[x][2], acc[x][3]));
     }
-    float4 hs = f4(0.f);
-    for (int task = tid; task < n * 4; task += NT) hs = hs + ld4(g.H + (task >> 2) * 16 + q * 4);
     block_sum_q4(hs, sRed, sV + V_TMP16);        // barriers inside publish redbuf
     if (tid < 384) {
       const int c = tid / 24, f = tid % 24;

@@ -37,6 +37,8 @@ for i in [1, 2, 3, 4, 5, 6, 7, 8, 9, 20, 10, 11, 12, 14, 15, 16, 17, 18, 19, 21]
     print(f"{i:3d} {NAMES.get(i, ''):28s} {st[i] - prev:8d} cycles  {100.0 * (st[i] - prev) / tot:5.1f}%")
     prev = st[i]
 print("total", tot, "cycles")
+if st[46:62].any():
+    print("warp probe (cycles after stamp 1):", [int(x - st[1]) for x in st[46:62]])
 busy = st[64:64 + eng.grid]; pro = st[224:224 + eng.grid]
 print(f"per-CTA busy cycles: max {busy.max()}  mean {busy.mean():.0f}  min {busy.min()}  (balance {busy.mean() / busy.max():.2f});"
       f" launch prologue mean {pro.mean():.0f} max {pro.max()}")
