@@ -308,13 +308,16 @@ def main():
             ev.record()
         n_e2e = max(3, min(args.steps, 20))
         h2d = 0
+        # the ranks of one node share its host cores: each packer gets its share (0 = all CPUs of this process, <= 32)
+        local_world = int(os.environ.get("LOCAL_WORLD_SIZE", world))
+        pack_threads = 0 if local_world <= 1 else max(2, min(32, len(os.sched_getaffinity(0)) // local_world))
         pool_ex = ThreadPoolExecutor(1)
 
         def pack_job(i):
             j = i & 1
             ev_h2d[j].synchronize()                                  # the previous upload from this pinned buffer is over
             lo = (i % args.pool) * BATCH
-            b = pk(states[lo:lo + BATCH], blob.n_cap, blob.e_cap, out_host=host_bufs[j])
+            b = pk(states[lo:lo + BATCH], blob.n_cap, blob.e_cap, threads=pack_threads, out_host=host_bufs[j])
             side_bufs[j][:BATCH * 2].copy_(torch.from_numpy(actions[lo:lo + BATCH].reshape(-1)))
             return b
 
@@ -335,8 +338,8 @@ def main():
         def e2e_step(i):
             nonlocal h2d
             j = i & 1
+            pending[i + 2] = pool_ex.submit(pack_job, i + 2)          # host packing two steps ahead (queued behind i+1)
             uploaded[i + 1] = upload(i + 1)                           # H2D of the next step, on the copy stream
-            pending[i + 2] = pool_ex.submit(pack_job, i + 2)          # host packing two steps ahead
             b = uploaded.pop(i)
             side = dev_sides[j]
             d = [side[:BATCH * 2]] + [side[BATCH * (2 + q):BATCH * (3 + q)] for q in range(4)]

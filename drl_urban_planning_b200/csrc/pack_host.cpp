@@ -2,6 +2,8 @@
 // Replaces tensorfy + batch_data of the reference (urban_planning_agent.py:16-20, state_encoder.py:163-177).
 #include <algorithm>
 #include <atomic>
+#include <chrono>
+#include <memory>
 #include <condition_variable>
 #include <cstdio>
 #include <cstring>
@@ -12,6 +14,7 @@
 #include <vector>
 
 #include <pthread.h>
+#include <sched.h>
 #if defined(__SSE2__)
 #include <emmintrin.h>
 #endif
@@ -66,7 +69,9 @@ inline int count_set(const uint8_t* m, int lo, int hi) {
 }
 
 // Validates one state against the layout contract and returns its sizes.  Returns nullptr or an error text.
-const char* measure_one(const StateView& s, int n_cap, int e_cap, Counts* out) {
+// `check_edges`: upb_pack_fill checks the edge endpoints while it builds the CSR (one read of the edge list instead of
+// two), upb_pack_measure checks them here.
+const char* measure_one(const StateView& s, int n_cap, int e_cap, bool check_edges, Counts* out) {
   for (int j = 0; j < 9; ++j)
     if (((const void* const*)&s)[j] == nullptr) return "null array pointer";
   bool pn, pe;
@@ -78,8 +83,8 @@ const char* measure_one(const StateView& s, int n_cap, int e_cap, Counts* out) {
   if (s.stage[0] != 0.f && s.stage[1] == 0.f) stage = 0;
   else if (s.stage[1] != 0.f && s.stage[0] == 0.f) stage = 1;
   else return "stage must be one-hot on 'land_use' or 'road' (stored states are pre-step states)";
-  {  // every endpoint of a real edge is a real node: unsigned compare catches negatives too; no early exit so the
-     // loop vectorises
+  if (check_edges) {  // every endpoint of a real edge is a real node: unsigned compare catches negatives too; no
+                      // early exit so the loop vectorises
     const uint64_t lim = (uint64_t)n;
     const uint64_t* ei = (const uint64_t*)s.edge_index;
     uint64_t bad = 0;
@@ -143,9 +148,19 @@ struct Plan {
 };
 
 // Persistent worker pool.  The packer runs once per PPO minibatch in the end-to-end path; spawning threads per call
-// (tens of microseconds each) cost more than the packing itself.  Workers sleep on a condition variable between jobs.
+// (tens of microseconds each) cost more than the packing itself.  Design points, all measured on the bench host:
+//  * a job is finished when all its ITEMS are done, not when every helper has checked in: a helper that the kernel
+//    wakes late simply finds nothing left (its shared_ptr keeps the finished job's counters alive);
+//  * helpers poll for the next job for a short while before they sleep on the condition variable, so the second
+//    pass of a pack call (fill, right after measure) starts on warm threads without a second wake-up ramp.
 // The pool is leaked on purpose (detached threads, no static destructor order problems) and rebuilt lazily in a forked
 // child (the reference forks rollout workers, khrylib/rl/agents/agent.py:83-89; worker threads do not survive a fork).
+inline void cpu_relax() {
+#if defined(__SSE2__)
+  _mm_pause();
+#endif
+}
+
 class Pool {
  public:
   static Pool* get() {
@@ -164,70 +179,93 @@ class Pool {
     std::lock_guard<std::mutex> serial(run_mu_);
     threads = std::min(threads, (count + chunk - 1) / chunk);
     grow(threads - 1);
+    auto job = std::make_shared<Job>();
+    job->fn = fn; job->ctx = ctx; job->count = count; job->chunk = chunk; job->max_helpers = threads - 1;
+    bool wake;
     {
       std::lock_guard<std::mutex> lk(mu_);
-      fn_ = fn; ctx_ = ctx; count_ = count; chunk_ = chunk;
-      next_.store(0, std::memory_order_relaxed);
-      helpers_ = threads - 1;
-      pending_ = threads - 1;
-      ++epoch_;
+      job_ = job;
+      epoch_.fetch_add(1, std::memory_order_release);
+      wake = sleepers_ > 0;
     }
-    if (threads > 1) cv_work_.notify_all();
-    work();
-    if (threads > 1) {
-      std::unique_lock<std::mutex> lk(mu_);
-      cv_done_.wait(lk, [&] { return pending_ == 0; });
+    if (wake) cv_.notify_all();
+    work(*job);
+    for (int spins = 0; job->done.load(std::memory_order_acquire) < count; ++spins) {   // chunks still in other hands
+      if (spins > 2000) std::this_thread::yield();
+      else cpu_relax();
     }
   }
 
  private:
+  struct Job {
+    void (*fn)(void*, int) = nullptr;
+    void* ctx = nullptr;
+    int count = 0, chunk = 1, max_helpers = 0;
+    std::atomic<int> next{0}, done{0}, joined{0};
+  };
+
   static Pool*& instance() { static Pool* p = nullptr; return p; }
   static std::mutex& global_mu() { static std::mutex* m = new std::mutex(); return *m; }
 
-  void work() {
+  static void work(Job& j) {
     for (;;) {
-      const int lo = next_.fetch_add(chunk_, std::memory_order_relaxed);
-      if (lo >= count_) break;
-      const int hi = std::min(count_, lo + chunk_);
-      for (int i = lo; i < hi; ++i) fn_(ctx_, i);
+      const int lo = j.next.fetch_add(j.chunk, std::memory_order_relaxed);
+      if (lo >= j.count) break;
+      const int hi = std::min(j.count, lo + j.chunk);
+      for (int i = lo; i < hi; ++i) j.fn(j.ctx, i);
+      j.done.fetch_add(hi - lo, std::memory_order_release);
+    }
+  }
+
+  void helper() {
+    uint64_t seen = 0;
+    for (;;) {
+      bool got = false;
+      const auto until = std::chrono::steady_clock::now() + std::chrono::microseconds(50);
+      for (int it = 0;; ++it) {
+        if (epoch_.load(std::memory_order_acquire) != seen) { got = true; break; }
+        if ((it & 63) == 63 && std::chrono::steady_clock::now() > until) break;
+        cpu_relax();
+      }
+      std::shared_ptr<Job> job;
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        if (!got) {
+          ++sleepers_;
+          cv_.wait(lk, [&] { return epoch_.load(std::memory_order_acquire) != seen; });
+          --sleepers_;
+        }
+        seen = epoch_.load(std::memory_order_acquire);
+        job = job_;
+      }
+      if (job && job->joined.fetch_add(1, std::memory_order_relaxed) < job->max_helpers) work(*job);
     }
   }
 
   void grow(int want) {
-    while ((int)started_ < want) {
-      const int id = started_++;
-      std::thread([this, id] {
-        uint64_t seen = 0;
-        for (;;) {
-          {
-            std::unique_lock<std::mutex> lk(mu_);
-            cv_work_.wait(lk, [&] { return epoch_ != seen; });
-            seen = epoch_;
-            if (id >= helpers_) continue;      // this job wants fewer helpers
-          }
-          work();
-          {
-            std::lock_guard<std::mutex> lk(mu_);
-            if (--pending_ == 0) cv_done_.notify_one();
-          }
-        }
-      }).detach();
+    while (started_ < want) {
+      ++started_;
+      std::thread([this] { helper(); }).detach();
     }
   }
 
   std::mutex run_mu_, mu_;
-  std::condition_variable cv_work_, cv_done_;
-  void (*fn_)(void*, int) = nullptr;
-  void* ctx_ = nullptr;
-  int count_ = 0, chunk_ = 1, helpers_ = 0, pending_ = 0, started_ = 0;
-  uint64_t epoch_ = 0;
-  std::atomic<int> next_{0};
+  std::condition_variable cv_;
+  std::shared_ptr<Job> job_;            // guarded by mu_
+  std::atomic<uint64_t> epoch_{0};      // bumped under mu_, polled without it
+  int sleepers_ = 0;                    // guarded by mu_
+  int started_ = 0;                     // guarded by run_mu_
 };
 
 template <class F>
 void parallel_for(int count, int threads, F&& fn) {
   // copy-bound work: a couple of dozen threads saturate the host memory system
-  if (threads <= 0) threads = (int)std::min(32u, std::max(1u, std::thread::hardware_concurrency()));
+  if (threads <= 0) {   // CPUs this process may run on (affinity mask / container limits), not the machine's count
+    cpu_set_t set;
+    int avail = (int)std::thread::hardware_concurrency();
+    if (sched_getaffinity(0, sizeof(set), &set) == 0) avail = CPU_COUNT(&set);
+    threads = std::min(32, std::max(1, avail));
+  }
   constexpr int kChunk = 4;
   threads = std::min(threads, std::max(1, count / (2 * kChunk)));
   if (threads <= 1) {
@@ -238,7 +276,7 @@ void parallel_for(int count, int threads, F&& fn) {
   Pool::get()->run(count, threads, kChunk, [](void* c, int i) { (*static_cast<Fn*>(c))(i); }, (void*)&fn);
 }
 
-int make_plan(int count, const void* const* arrays, int n_cap, int e_cap, int threads, Plan* plan) {
+int make_plan(int count, const void* const* arrays, int n_cap, int e_cap, int threads, bool check_edges, Plan* plan) {
   if (count < 0 || (count > 0 && arrays == nullptr)) return set_error(UPB_ERR_ARG, "pack: bad count / arrays");
   if (n_cap < 1 || n_cap > 65535 || e_cap < 0 || 2 * (int64_t)e_cap > 65535)
     return set_error(UPB_ERR_ARG, "pack: caps must satisfy n_cap <= 65535 and 2*e_cap <= 65535");
@@ -246,7 +284,7 @@ int make_plan(int count, const void* const* arrays, int n_cap, int e_cap, int th
   std::atomic<int> bad{-1};
   std::vector<const char*> why(count, nullptr);
   parallel_for(count, threads, [&](int i) {
-    why[i] = measure_one(view(arrays, i), n_cap, e_cap, &plan->counts[i]);
+    why[i] = measure_one(view(arrays, i), n_cap, e_cap, check_edges, &plan->counts[i]);
     if (why[i]) {
       int expected = -1;
       bad.compare_exchange_strong(expected, i);
@@ -307,7 +345,8 @@ int make_plan(int count, const void* const* arrays, int n_cap, int e_cap, int th
 }
 
 // One graph's sections are built in per-thread scratch (cache resident) and streamed to the blob.
-void fill_one(const StateView& s, const GraphDesc& d, const BlobHeader& h, uint8_t* blob, int index) {
+// Returns nullptr or an error text (edge endpoints are validated here, see measure_one).
+const char* fill_one(const StateView& s, const GraphDesc& d, const BlobHeader& h, uint8_t* blob, int index) {
   const int n = d.n, e = d.e;
   stream_rows((float*)(blob + h.off_x) + (size_t)d.x_row * kNodeStride, s.node_features, n);
   {
@@ -321,7 +360,7 @@ void fill_one(const StateView& s, const GraphDesc& d, const BlobHeader& h, uint8
   const int rp_len = (n + 1 + 7) & ~7, adj_len = (2 * e + 3) & ~3, cand_len = (d.k + 3) & ~3;
   const int slots = d.ord_rounds * kPullWarps * kPullGroup;
   static thread_local std::vector<uint32_t> scratch;
-  const size_t need = 3 * (size_t)(n + 2) + (size_t)rp_len / 2 + adj_len + 2 * (size_t)cand_len + (size_t)slots / 2 + 64;
+  const size_t need = 3 * (size_t)(n + 2) + (size_t)rp_len / 2 + adj_len + 2 * (size_t)cand_len + (size_t)slots / 2 + e + 64;
   if (scratch.size() < need) scratch.resize(need);
   // 16-byte aligned carve-up (the vector's storage is at least 16-byte aligned; every length below is a multiple of 4 words)
   uint32_t* base = scratch.data();
@@ -332,12 +371,26 @@ void fill_one(const StateView& s, const GraphDesc& d, const BlobHeader& h, uint8
   uint16_t* ord = (uint16_t*)base;                  base += slots / 2;
   int* pos = (int*)base;                            base += n + 2;      // [n + 1]
   int* idx = (int*)base;                            base += n + 2;      // [n] nodes by descending degree
-  int* bucket = (int*)base;                                             // [n + 2]
-  // degree count -> CSR row pointers over the symmetrised adjacency
+  int* bucket = (int*)base;                         base += n + 2;      // [n + 2]
+  uint32_t* euv = base;                                                 // [e] u | v << 16: the edge list, compact
+  // One pass over the int64 edge list: endpoint check (unsigned compare catches negatives), compact copy, degree
+  // count -> CSR row pointers over the symmetrised adjacency.  Out-of-range endpoints are clamped so that nothing is
+  // written out of bounds before the error is reported.
   memset(pos, 0, sizeof(int) * (n + 1));
-  for (int j = 0; j < e; ++j) {
-    pos[(int)s.edge_index[2 * j] + 1]++;
-    pos[(int)s.edge_index[2 * j + 1] + 1]++;
+  {
+    const uint64_t* ei = (const uint64_t*)s.edge_index;
+    const uint64_t lim = (uint64_t)n;
+    uint64_t bad = 0;
+    for (int j = 0; j < e; ++j) {
+      uint64_t u = ei[2 * j], v = ei[2 * j + 1];
+      bad |= (uint64_t)(u >= lim) | (uint64_t)(v >= lim);
+      u = u < lim ? u : lim - 1;
+      v = v < lim ? v : lim - 1;
+      euv[j] = (uint32_t)u | ((uint32_t)v << 16);
+      pos[u + 1]++;
+      pos[v + 1]++;
+    }
+    if (bad) return "a real edge joins a padded node";
   }
   {  // stable counting sort by descending degree (degrees above n land in the top bucket; ties keep node order)
     const int top = n;
@@ -370,7 +423,7 @@ void fill_one(const StateView& s, const GraphDesc& d, const BlobHeader& h, uint8
   }
   int slot = 0;
   for (int j = 0; j < e; ++j) {
-    const uint32_t u = (uint32_t)s.edge_index[2 * j], v = (uint32_t)s.edge_index[2 * j + 1];
+    const uint32_t u = euv[j] & 0xffffu, v = euv[j] >> 16;
     uint32_t tag = 0;
     if (d.stage == 0 && s.land_use_mask[j]) {
       cuv[slot] = u | (v << 16);
@@ -397,6 +450,7 @@ void fill_one(const StateView& s, const GraphDesc& d, const BlobHeader& h, uint8
   stream_copy((uint32_t*)(blob + h.off_cand_uv) + d.cand_off, cuv, sizeof(uint32_t) * cand_len);
   stream_copy((int32_t*)(blob + h.off_cand_idx) + d.cand_off, cidx, sizeof(int32_t) * cand_len);
   stream_fence();       // streaming stores are weakly ordered: make them visible before the job is reported done
+  return nullptr;
 }
 
 }  // namespace
@@ -409,7 +463,7 @@ extern "C" int upb_pack_measure(int count, const void* const* state_arrays, int 
                                 uint64_t* blob_bytes) {
   if (!blob_bytes) return set_error(UPB_ERR_ARG, "pack_measure: blob_bytes is null");
   Plan plan;
-  int rc = make_plan(count, state_arrays, n_cap, e_cap, threads, &plan);
+  int rc = make_plan(count, state_arrays, n_cap, e_cap, threads, true, &plan);
   if (rc != UPB_OK) return rc;
   *blob_bytes = plan.hdr.total_bytes;
   return UPB_OK;
@@ -419,13 +473,27 @@ extern "C" int upb_pack_fill(int count, const void* const* state_arrays, int n_c
                              void* blob_host, uint64_t blob_bytes) {
   if (!blob_host || ((uintptr_t)blob_host & 15)) return set_error(UPB_ERR_ARG, "pack_fill: blob must be 16-byte aligned");
   Plan plan;
-  int rc = make_plan(count, state_arrays, n_cap, e_cap, threads, &plan);
+  int rc = make_plan(count, state_arrays, n_cap, e_cap, threads, false, &plan);
   if (rc != UPB_OK) return rc;
   if (blob_bytes < plan.hdr.total_bytes) return set_error(UPB_ERR_CAPACITY, "pack_fill: blob buffer too small");
   uint8_t* blob = (uint8_t*)blob_host;
   memcpy(blob, &plan.hdr, sizeof(BlobHeader));
   if (count > 0) memcpy(blob + plan.hdr.off_desc, plan.desc.data(), sizeof(GraphDesc) * (size_t)count);
-  parallel_for(count, threads, [&](int i) { fill_one(view(state_arrays, i), plan.desc[i], plan.hdr, blob, i); });
+  std::atomic<int> bad{count};
+  std::atomic<const char*> why{nullptr};
+  parallel_for(count, threads, [&](int i) {
+    const char* err = fill_one(view(state_arrays, i), plan.desc[i], plan.hdr, blob, i);
+    if (err) {
+      int cur = bad.load();
+      while (i < cur && !bad.compare_exchange_weak(cur, i)) {}
+      why.store(err);
+    }
+  });
+  if (bad.load() < count) {
+    char buf[256];
+    snprintf(buf, sizeof(buf), "pack: state %d: %s", bad.load(), why.load());
+    return set_error(UPB_ERR_FORMAT, buf);
+  }
   return UPB_OK;
 }
 

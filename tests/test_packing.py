@@ -113,3 +113,53 @@ def test_pack_rejects_contract_violations(breaker, msg):
     breaker(st)
     with pytest.raises(_lib.UpbError, match=msg):
         pack_states([st], pinned=False)
+
+
+def test_fill_in_place_path_validates_edges():
+    """With a caller-provided buffer the packer skips the measuring pass; the edge endpoints are then checked while the
+    CSR is built (one read of the edge list), including negative indices, and nothing is written out of bounds."""
+    import torch
+    states, _ = synth.make_states(3, "tiny", 20)
+    ref = pack_states(states, pinned=False)
+    out = torch.empty(ref.nbytes + 4096, dtype=torch.uint8)
+    same = pack_states(states, ref.n_cap, ref.e_cap, out_host=out)
+    assert same.nbytes == ref.nbytes and np.array_equal(host_bytes(same)[:ref.nbytes], host_bytes(ref)[:ref.nbytes])
+    for bad_value in (-1, 47, 2 ** 40):
+        broken = [list(s) for s in states]
+        broken[13][2] = broken[13][2].copy()
+        broken[13][2][0, 1] = bad_value
+        with pytest.raises(_lib.UpbError, match="state 13.*padded node"):
+            pack_states(broken, ref.n_cap, ref.e_cap, out_host=out)
+
+
+def test_pack_from_concurrent_threads_and_after_fork():
+    """The worker pool is shared by all callers of a process and must be rebuilt in a forked child (the reference forks
+    its rollout workers, khrylib/rl/agents/agent.py:83-89)."""
+    import os, threading
+    states, _ = synth.make_states(7, "small", 64)
+    ref = pack_states(states, threads=1, pinned=False)
+    want = host_bytes(ref)[:ref.nbytes].tobytes()
+    errors = []
+
+    def job():
+        try:
+            for _ in range(10):
+                b = pack_states(states, threads=4, pinned=False)
+                assert host_bytes(b)[:b.nbytes].tobytes() == want
+        except Exception as ex:      # pragma: no cover
+            errors.append(ex)
+
+    ts = [threading.Thread(target=job) for _ in range(3)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errors
+    pid = os.fork()
+    if pid == 0:
+        ok = 1
+        try:
+            b = pack_states(states, threads=4, pinned=False)
+            ok = 0 if host_bytes(b)[:b.nbytes].tobytes() == want else 2
+        finally:
+            os._exit(ok)
+    _, status = os.waitpid(pid, 0)
+    assert os.WEXITSTATUS(status) == 0

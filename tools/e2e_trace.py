@@ -58,8 +58,8 @@ pending[1] = pool_ex.submit(pack_job, 1)
 for i in range(12):
     j = i & 1
     a = now()
-    uploaded[i + 1] = upload(i + 1)
     pending[i + 2] = pool_ex.submit(pack_job, i + 2)
+    uploaded[i + 1] = upload(i + 1)
     b = uploaded.pop(i)
     torch.cuda.current_stream().wait_event(ev_h2d[j])
     c = now()
