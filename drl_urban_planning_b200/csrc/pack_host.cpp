@@ -6,6 +6,7 @@
 #include <memory>
 #include <condition_variable>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -242,10 +243,50 @@ class Pool {
     }
   }
 
+  // CPUs of the NUMA node the calling thread runs on (empty set if unknown).  The states and the pinned staging
+  // buffer were normally first-touched by that thread, so helpers on the same node read and write local memory.
+  static bool node_cpus(cpu_set_t* out) {
+    const int cpu = sched_getcpu();
+    if (cpu < 0) return false;
+    for (int node = 0; node < 64; ++node) {
+      char path[96];
+      snprintf(path, sizeof(path), "/sys/devices/system/node/node%d/cpulist", node);
+      FILE* f = fopen(path, "r");
+      if (!f) return false;
+      char buf[4096];
+      const bool ok = fgets(buf, sizeof(buf), f) != nullptr;
+      fclose(f);
+      if (!ok) return false;
+      CPU_ZERO(out);
+      bool mine = false;
+      for (char* p = buf; *p;) {
+        char* end;
+        long a = strtol(p, &end, 10), b = a;
+        if (end == p) break;
+        if (*end == '-') { p = end + 1; b = strtol(p, &end, 10); }
+        for (long c = a; c <= b && c < CPU_SETSIZE; ++c) { CPU_SET((int)c, out); mine |= (c == cpu); }
+        p = (*end == ',') ? end + 1 : end;
+        if (*end != ',') break;
+      }
+      if (mine) return true;
+    }
+    return false;
+  }
+
   void grow(int want) {
+    if (started_ >= want) return;
+    cpu_set_t node, allowed, both;
+    bool pin = false;
+    const char* env = getenv("UPB_PACK_NUMA");
+    if (!(env && env[0] == '0') && node_cpus(&node) && sched_getaffinity(0, sizeof(allowed), &allowed) == 0) {
+      CPU_AND(&both, &node, &allowed);
+      pin = CPU_COUNT(&both) >= 2 && CPU_COUNT(&both) < CPU_COUNT(&allowed);     // a real choice, and not a tiny set
+    }
     while (started_ < want) {
       ++started_;
-      std::thread([this] { helper(); }).detach();
+      std::thread th([this] { helper(); });
+      if (pin) pthread_setaffinity_np(th.native_handle(), sizeof(both), &both);
+      th.detach();
     }
   }
 
@@ -266,7 +307,7 @@ void parallel_for(int count, int threads, F&& fn) {
     if (sched_getaffinity(0, sizeof(set), &set) == 0) avail = CPU_COUNT(&set);
     threads = std::min(32, std::max(1, avail));
   }
-  constexpr int kChunk = 4;
+  static const int kChunk = [] { const char* e = getenv("UPB_PACK_CHUNK"); const int v = e ? atoi(e) : 1; return v < 1 ? 1 : v; }();
   threads = std::min(threads, std::max(1, count / (2 * kChunk)));
   if (threads <= 1) {
     for (int i = 0; i < count; ++i) fn(i);
