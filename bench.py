@@ -177,6 +177,7 @@ def main():
     ap.add_argument("--pool", type=int, default=16, help="minibatches resident in HBM (16 x 11.5 MB > 126 MB L2)")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--nccl-exchange", action="store_true", help="multi-GPU: all-reduce the gradients with NCCL instead of the in-kernel peer exchange")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -226,10 +227,16 @@ def main():
                         for m in range(args.pool)], dtype=np.float64)
     grad = eng.new_grad_buffer()
     gB, gI = BATCH * world, BATCH * world
+    # multi-GPU: the ranks' gradient sums are exchanged inside the step kernel through peer memory (NVLink) when the
+    # peers' buffers can be mapped; --nccl-exchange keeps one ncclAllReduce + upb_apply per step instead
+    fused_exchange = world > 1 and not args.nccl_exchange and eng.connect_peers()
     setup_s = time.time() - t0
 
     def step(i):
         if world == 1:      # gradient + cross-CTA reduction + Adam in one launch
+            eng.ppo_step(blob, params, act, adv, ret, fixed, exps, 1.0 / gB, 1.0 / gI, ids=mb_ids[i % args.pool], out=grad)
+            return
+        if fused_exchange and eng.next_step_fused():      # cross-rank sum inside the kernel (peer memory), one launch
             eng.ppo_step(blob, params, act, adv, ret, fixed, exps, 1.0 / gB, 1.0 / gI, ids=mb_ids[i % args.pool], out=grad)
             return
         eng.ppo_grad(blob, params, act, adv, ret, fixed, exps, 1.0 / gB, 1.0 / gI, ids=mb_ids[i % args.pool], out=grad)
@@ -347,9 +354,12 @@ def main():
             if world == 1:
                 eng.ppo_step(b, params, d[0], d[1], d[2], d[3], d[4], 1.0 / gB, 1.0 / gI, out=grad)
             else:
-                eng.ppo_grad(b, params, d[0], d[1], d[2], d[3], d[4], 1.0 / gB, 1.0 / gI, out=grad)
-                dist.all_reduce(grad, op=dist.ReduceOp.SUM)
-                eng.apply(params, grad)
+                if fused_exchange and eng.next_step_fused():
+                    eng.ppo_step(b, params, d[0], d[1], d[2], d[3], d[4], 1.0 / gB, 1.0 / gI, out=grad)
+                else:
+                    eng.ppo_grad(b, params, d[0], d[1], d[2], d[3], d[4], 1.0 / gB, 1.0 / gI, out=grad)
+                    dist.all_reduce(grad, op=dist.ReduceOp.SUM)
+                    eng.apply(params, grad)
             ev_done[j].record()
             eng.read_losses(grad)                                     # D2H of the step's result (synchronises)
             h2d = b.nbytes + 4 * (BATCH * 2 + BATCH * 4)
@@ -370,7 +380,7 @@ def main():
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         e2e = {"value": BATCH * world * n_e2e / float(dt.item()), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": 32, "steps": n_e2e,
-               "path": "reference-layout host states -> upb_pack_fill -> pinned -> H2D (copy stream) -> upb_ppo_step -> D2H losses; "
+               "path": "reference-layout host states -> upb_pack_fill -> pinned -> H2D (copy stream) -> upb_ppo_step (N > 1 without peer access: upb_ppo_grad, all-reduce, upb_apply) -> D2H losses; "
                        "packer, upload and step of consecutive minibatches overlap"}
 
     # ---- CPU baseline beside it (rank 0, N=1): oracle port of the reference's padded eager dataflow
@@ -392,6 +402,9 @@ def main():
             "config": {"workload": f"{args.community} (cfg {args.community}), PPO minibatch update, {BATCH} rollout graphs per GPU "
                                    f"per step, caps {blob.n_cap}/{blob.e_cap}, mean n={info[:, 0].mean():.0f} e={info[:, 1].mean():.0f}",
                        "global_batch": BATCH * world, "parallelism": f"dp{world}",
+                       "gradient_exchange": ("none (one GPU)" if world == 1 else
+                                             "inside the step kernel, peer memory over NVLink" if fused_exchange else
+                                             "ncclAllReduce of the 55 KB gradient buffer + upb_apply"),
                        "l2_policy": f"inputs larger than L2: {args.pool} resident minibatches = {blob.nbytes / 1e6:.0f} MB cycled"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": read_traffic(), "kernel": "k_sgnn<TRAIN>", "kernel_ms": k_avg_ms,

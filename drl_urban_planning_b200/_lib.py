@@ -59,8 +59,12 @@ _PROTOS = {
     "upb_grid_size": (C.c_int, [_VP]),
     "upb_set_stamp_buffer": (C.c_int, [_VP, _VP]),
     "upb_launch_count": (C.c_int64, [_VP]),
+    "upb_peer_export": (C.c_int, [_VP, _VP]),
+    "upb_peer_connect": (C.c_int, [_VP, C.c_int, C.c_int, _VP]),
+    "upb_next_step_fused": (C.c_int, [_VP]),
 }
 EXPORTED_SYMBOLS = tuple(_PROTOS)
+UPB_PEER_HANDLE_BYTES = 64
 
 
 def lib() -> C.CDLL:

@@ -188,6 +188,11 @@ struct StepArgs {
   long long* steps_out;        // [4]
   unsigned int* gridbar;       // [3] two arrival counters + stage bits, zero between launches
   float lr, beta1, beta2, adam_eps;
+  // multi-GPU fused tail (upb_peer_connect): the per-rank column sums are exchanged through peer memory (NVLink) inside
+  // the kernel.  xchg layout per rank (floats): [2 parities][G_ROW] sums, then [2][2][MAX_PEERS] u32: sequence flags | stage bits.
+  int world, rank;
+  unsigned int seq;            // exchange sequence number of this step (same on all ranks, starts at 1)
+  float* const* peers;         // device array [world] of the ranks' exchange buffers (own buffer at [rank])
   long long* stamps;   // optional [384]: [0,64) clock64() phase stamps, [64,224) busy cycles per CTA, [224,384) prologue cycles; of the first graph of CTA 0 (tools/phase_times.py)
 };
 
@@ -1109,6 +1114,12 @@ __device__ __forceinline__ void softmax_seeds(const StepArgs& a, const BlobHeade
       a.stamps[46 + (threadIdx.x >> 5)] = clock64();                                                         \
   } while (0)
 
+#define UPB_WSTAMP_B()                                                                                       \
+  do {                                                                                                       \
+    if (a.stamps != nullptr && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && first_item && threadIdx.x < 384) \
+      a.stamps[212 + (threadIdx.x >> 5)] = clock64();                                                        \
+  } while (0)
+
 template <bool TRAIN, bool BIG>
 __device__ void graph_body(const StepArgs& a, const BlobHeader& hd, const GraphDesc& d, int gid, float* smem,
                            float* gp, float* scr, bool first_item) {
@@ -1230,6 +1241,7 @@ __device__ void graph_body(const StepArgs& a, const BlobHeader& hd, const GraphD
     for (int f = 0; f < 24; ++f) w[f] = *reinterpret_cast<const float2*>(sW + S_WET + f * 16 + c2);
     const float2 be = *reinterpret_cast<const float2*>(sW + S_BE + c2);
     const float* xs = smem + S_EPQ;
+    UPB_WSTAMP_B();
     for (int i = warp * 4 + (lane >> 3); i < n; i += NW * 4) {
       const float4* xr = reinterpret_cast<const float4*>(xs + i * FS);
       float2 acc = be;
@@ -1373,13 +1385,17 @@ __device__ void graph_body(const StepArgs& a, const BlobHeader& hd, const GraphD
   UPB_STAMP(9);
   // softmax / outputs / PPO seeds by warp NW-1; meanwhile (TRAIN) warps 0..7 run the value-head and numeric-encoder
   // backward, which only needs the value
+  // (code order: the eight value-backward warps fall straight into their work; the softmax warp's 30 KB of code come
+  // last, so only idle warps branch over them)
+  if constexpr (TRAIN) {
+    if (warp < 8) {
+      const float gV = 2.f * a.c_value * (sc[SC_VALUE] - sc[SC_RET]) * a.inv_batch;
+      value_numeric_bwd_group(sV, vn, gV, gp, tid);
+    }
+    if (tid >= 256 && tid < 272) sV[V_GHC + tid - 256] = 0.f;
+  }
   if (warp == NW - 1) softmax_seeds<TRAIN>(a, hd, g, sc, gp, lane);
   if constexpr (!TRAIN) return;
-  if (warp < 8) {
-    const float gV = 2.f * a.c_value * (sc[SC_VALUE] - sc[SC_RET]) * a.inv_batch;
-    value_numeric_bwd_group(sV, vn, gV, gp, tid);
-  }
-  if (tid >= 256 && tid < 272) sV[V_GHC + tid - 256] = 0.f;
   __syncthreads();
   UPB_STAMP(10);
 
@@ -1711,6 +1727,24 @@ __device__ __forceinline__ void grid_wait(unsigned int* ctr, unsigned int target
   __syncthreads();
 }
 
+// ---- cross-GPU exchange (one process per GPU, peers opened with CUDA IPC over NVLink / NVSwitch) ---------------------
+constexpr int MAX_PEERS = 16;
+constexpr int XCHG_FLAGS = 2 * G_ROW;          // float offset of the flag words inside an exchange buffer
+constexpr unsigned PEER_SPIN_LIMIT = 1u << 22; // polls before a rank gives up on a peer (seconds; flags the step invalid)
+__device__ __forceinline__ float ld_sys(const float* p) {
+  float v;
+  asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 // torch.optim.Adam on one element with torch's operation order (same arithmetic as k_apply; no clipping here).
 // m, v, p are the element's current moments / value (loaded early by the caller so the latency overlaps).
 __device__ __forceinline__ void adam_elem(const StepArgs& a, int i, float g, float m, float v, float p, float step_size,
@@ -1878,6 +1912,217 @@ __device__ void fused_tail(const StepArgs& a, float* smem, unsigned stage_bits) 
   UPB_TSTAMP(44);
 }
 
+// Multi-GPU variant of the fused tail (a.world > 1): data-parallel ranks, each with its own shard of the minibatch.
+//   barrier 1 (local)  -> every CTA sums its 128 columns over the local CTAs into this rank's exchange buffer
+//   barrier 2 (local)  -> CTA 0 publishes this rank's stage bits and "rank r, step seq ready" into every rank's flag rows
+//                         (st.release.sys over NVLink)
+//   every CTA polls its OWN rank's flag row (local memory) until all ranks are ready, then sums its columns over the
+//   ranks in rank order (peer loads) and applies Adam; CTA 0 also sums the 816 virtual attention gradients itself and
+//   chains them.  Same summation order on every rank -> bit-identical parameters everywhere, no NCCL call, one launch
+//   per optimiser step.  The exchange buffer is double-buffered by step parity: a rank can only be one step ahead of
+//   the slowest one (it needs that rank's flag of the current step), so parity p is never rewritten while it is read.
+__device__ void fused_tail_peers(const StepArgs& a, float* smem, unsigned stage_bits) {
+  constexpr int COLS = 128;
+  const int tid = threadIdx.x;
+  const int nparts = gridDim.x;
+  const int world = a.world;
+  __shared__ float sh_adam[12];
+  __shared__ long long sh_steps[6];
+  __shared__ int sh_live[2];
+  __shared__ int sh_timeout;
+  __shared__ const float* sh_peer[MAX_PEERS];
+  const unsigned par = a.seq & 1u;
+  if (tid < world) sh_peer[tid] = a.peers[tid] + (size_t)par * G_ROW;
+  if (tid == 32) { sh_timeout = 0; sh_live[0] = 0; sh_live[1] = 0; }
+  if (tid < 6) {
+    const int seg = tid >> 1, live = tid & 1;
+    const long long stp = a.steps_in[1 + seg] + live;
+    const double bc1 = 1.0 - ipow((double)a.beta1, stp > 0 ? stp : 1);
+    const double bc2 = 1.0 - ipow((double)a.beta2, stp > 0 ? stp : 1);
+    sh_adam[tid * 2 + 0] = (float)((double)a.lr / bc1);
+    sh_adam[tid * 2 + 1] = (float)sqrt(bc2);
+    sh_steps[tid] = stp;
+  }
+  float* xself = a.peers[a.rank] + (size_t)par * G_ROW;
+  if (tid == 0 && stage_bits) atomicOr(a.gridbar + 2, stage_bits);     // which policy heads this CTA's graphs used
+  const int col0 = blockIdx.x * COLS + (tid >> 2), part = tid & 3;
+  const bool attn0 = (col0 >= P_MHA_IN_W && col0 < P_MHA_OUT_W) || (col0 >= P_ATT_Q_W && col0 < P_LU_W0);
+  const bool real0 = part == 0 && col0 < NUM_PARAMS && !attn0;
+  float pm = 0.f, pv = 0.f, pp = 0.f;
+  if (real0) { pm = a.adam_m[col0]; pv = a.adam_v[col0]; pp = a.params_rw[col0]; }
+  float* sG = smem;
+  float* sWin = sG + 816;
+  float* sW3 = sWin + 768;
+  float* sB = sW3 + 768;
+  float* sOut = sB + 48;
+  const int pW[3] = {P_ATT_Q_W, P_ATT_K_W, P_ATT_V_W};
+  const int pB[3] = {P_ATT_Q_B, P_ATT_K_B, P_ATT_V_B};
+  float cm[4], cv[4], cp[4];
+  int cdst[4];
+  if (blockIdx.x == 0) {
+    const float* P = a.params_rw;
+    for (int i = tid; i < 768; i += NT) sWin[i] = P[P_MHA_IN_W + i];
+    if (tid < 256) { sW3[tid] = P[P_ATT_Q_W + tid]; sW3[256 + tid] = P[P_ATT_K_W + tid]; sW3[512 + tid] = P[P_ATT_V_W + tid]; }
+    if (tid < 16) { sB[tid] = P[P_ATT_Q_B + tid]; sB[16 + tid] = P[P_ATT_K_B + tid]; sB[32 + tid] = P[P_ATT_V_B + tid]; }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int i = tid + j * NT;
+      int dst = 0;
+      if (i < 768) dst = pW[i >> 8] + (i & 255);
+      else if (i < 1536) dst = P_MHA_IN_W + (i - 768);
+      else if (i < 1584) dst = pB[(i - 1536) >> 4] + ((i - 1536) & 15);
+      else if (i < 1632) dst = P_MHA_IN_B + (i - 1584);
+      cdst[j] = dst;
+      if (i < 1632) { cm[j] = a.adam_m[dst]; cv[j] = a.adam_v[dst]; cp[j] = P[dst]; }
+    }
+  }
+  grid_arrive(a.gridbar);
+  grid_wait(a.gridbar, gridDim.x);
+  // local column sums -> this rank's exchange buffer
+  for (int c0 = blockIdx.x * COLS; c0 < G_ROW; c0 += gridDim.x * COLS) {
+    const int col = c0 + (tid >> 2);
+    float s = 0.f;
+    if (col < G_ROW) {
+      const float* src = a.gpart + col;
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, s4 = 0.f, s5 = 0.f, s6 = 0.f, s7 = 0.f;
+      int r = part;
+      for (; r + 28 < nparts; r += 32) {
+        s0 += __ldcg(src + (size_t)r * G_ROW);        s1 += __ldcg(src + (size_t)(r + 4) * G_ROW);
+        s2 += __ldcg(src + (size_t)(r + 8) * G_ROW);  s3 += __ldcg(src + (size_t)(r + 12) * G_ROW);
+        s4 += __ldcg(src + (size_t)(r + 16) * G_ROW); s5 += __ldcg(src + (size_t)(r + 20) * G_ROW);
+        s6 += __ldcg(src + (size_t)(r + 24) * G_ROW); s7 += __ldcg(src + (size_t)(r + 28) * G_ROW);
+      }
+      for (; r < nparts; r += 4) s0 += __ldcg(src + (size_t)r * G_ROW);
+      s = ((s0 + s1) + (s2 + s3)) + ((s4 + s5) + (s6 + s7));
+    }
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    if (part == 0 && col < G_ROW) __stcg(xself + col, s);
+  }
+  grid_arrive(a.gridbar + 1);
+  if (blockIdx.x == 0) {
+    grid_wait(a.gridbar + 1, gridDim.x);            // every column of this rank is in its exchange buffer
+    if (tid < world) {                              // publish to rank `tid`: this rank's stage bits, then the step flag
+      unsigned bits;
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(bits) : "l"(a.gridbar + 2));
+      unsigned* row = reinterpret_cast<unsigned*>(a.peers[tid] + XCHG_FLAGS) + par * 2 * MAX_PEERS;
+      __threadfence_system();
+      asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(row + MAX_PEERS + a.rank), "r"(bits) : "memory");
+      st_release_sys(row + a.rank, a.seq);
+    }
+  }
+  if (tid < world) {                                // all ranks (this one included) have published this step
+    const unsigned* row = reinterpret_cast<const unsigned*>(a.peers[a.rank] + XCHG_FLAGS) + par * 2 * MAX_PEERS;
+    unsigned polls = 0;
+    while ((int)(ld_acquire_sys(row + tid) - a.seq) < 0) {
+      if (++polls >= PEER_SPIN_LIMIT) { sh_timeout = 1; break; }
+    }
+    unsigned bits;
+    asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(bits) : "l"(row + MAX_PEERS + tid));
+    if (bits & 1u) sh_live[0] = 1;                  // benign race: every writer stores 1
+    if (bits & 2u) sh_live[1] = 1;
+    __threadfence_system();
+  }
+  __syncthreads();
+  const bool live_lu = sh_live[0], live_rd = sh_live[1];
+  if (blockIdx.x == 0 && tid < 4) {
+    a.steps_out[tid] = tid == 0 ? a.steps_in[0] + 1
+                                : sh_steps[(tid - 1) * 2 + (tid == 1 ? 1 : (tid == 2 ? (live_lu ? 1 : 0) : (live_rd ? 1 : 0)))];
+  }
+  // All peer loads of a thread are issued before the first use: one NVLink round trip per phase, not one per rank.
+  float att0[MAX_PEERS], att1[MAX_PEERS];           // CTA 0: the ranks' virtual attention gradients tid and tid + NT
+  if (blockIdx.x == 0) {
+#pragma unroll
+    for (int p = 0; p < MAX_PEERS; ++p) {
+      att0[p] = 0.f; att1[p] = 0.f;
+      if (p < world) {
+        att0[p] = ld_sys(sh_peer[p] + G_QC + tid);
+        if (tid + NT < 816) att1[p] = ld_sys(sh_peer[p] + G_QC + tid + NT);
+      }
+    }
+  }
+  for (int c0 = blockIdx.x * COLS; c0 < G_ROW; c0 += gridDim.x * COLS) {
+    const int col = c0 + (tid >> 2);
+    if (part == 0 && col < G_ROW) {
+      float v[MAX_PEERS];
+#pragma unroll
+      for (int p = 0; p < MAX_PEERS; ++p) v[p] = p < world ? ld_sys(sh_peer[p] + col) : 0.f;
+      float s = 0.f;
+#pragma unroll
+      for (int p = 0; p < MAX_PEERS; ++p) s += v[p];                        // rank order: identical on every rank
+      if (col == G_STATS + 7 && sh_timeout) s += 1.f;                       // a peer never showed up: step is invalid
+      a.gsum[col] = s;
+      const bool attn = (col >= P_MHA_IN_W && col < P_MHA_OUT_W) || (col >= P_ATT_Q_W && col < P_LU_W0);
+      if (col < NUM_PARAMS && !attn) {
+        a.grad_out[col] = s;
+        int seg = 0;
+        bool live = true;
+        if (col >= P_LU_W0 && col < P_RD_W0) { seg = 1; live = live_lu; }
+        else if (col >= P_RD_W0 && col < POLICY_END) { seg = 2; live = live_rd; }
+        if (live) {
+          if (col != col0) { pm = a.adam_m[col]; pv = a.adam_v[col]; pp = a.params_rw[col]; }
+          adam_elem(a, col, s, pm, pv, pp, sh_adam[(seg * 2 + 1) * 2], sh_adam[(seg * 2 + 1) * 2 + 1]);
+        }
+      } else if (col >= NUM_PARAMS && col < UPB_STAT_OFFSET) {
+        a.grad_out[col] = 0.f;
+      }
+      if (col >= G_STATS && col < G_STATS + 8) a.grad_out[UPB_STAT_OFFSET + (col - G_STATS)] = s;
+      if (col >= G_STATS + 8 && col < G_STATS + UPB_STAT_COUNT) a.grad_out[UPB_STAT_OFFSET + (col - G_STATS)] = 0.f;
+    }
+  }
+  if (blockIdx.x != 0) return;
+  // CTA 0: virtual attention gradients summed over the ranks, chained to the six attention tensors, then their Adam
+  {
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int p = 0; p < MAX_PEERS; ++p) { s0 += att0[p]; s1 += att1[p]; }
+    sG[tid] = s0;
+    if (tid + NT < 816) sG[tid + NT] = s1;
+  }
+  __syncthreads();
+  if (tid < 256) {
+    const int r = tid >> 4, c = tid & 15;
+    const int gC[3] = {0, 272, 528};
+    const int gB[3] = {256, -1, 784};
+#pragma unroll
+    for (int s3 = 0; s3 < 3; ++s3) {
+      const float* Win = sWin + s3 * 256;
+      const float* gc = sG + gC[s3];
+      const float* W = sW3 + s3 * 256;
+      float ga = 0.f, gb = 0.f;
+#pragma unroll
+      for (int rr = 0; rr < 16; ++rr) {
+        ga = fmaf(Win[rr * 16 + r], gc[rr * 16 + c], ga);
+        gb = fmaf(gc[r * 16 + rr], W[c * 16 + rr], gb);
+      }
+      if (gB[s3] >= 0) gb = fmaf(sG[gB[s3] + r], sB[s3 * 16 + c], gb);
+      sOut[s3 * 256 + tid] = ga;
+      sOut[768 + s3 * 256 + tid] = gb;
+      if (tid < 16) {
+        float b1 = 0.f, b2 = 0.f;
+        if (gB[s3] >= 0) {
+          for (int rr = 0; rr < 16; ++rr) b1 = fmaf(Win[rr * 16 + tid], sG[gB[s3] + rr], b1);
+          b2 = sG[gB[s3] + tid];
+        }
+        sOut[1536 + s3 * 16 + tid] = b1;
+        sOut[1584 + s3 * 16 + tid] = b2;
+      }
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int i = tid + j * NT;
+    if (i < 1632) {
+      const float g = sOut[i];
+      a.grad_out[cdst[j]] = g;
+      adam_elem(a, cdst[j], g, cm[j], cv[j], cp[j], sh_adam[2], sh_adam[3]);
+    }
+  }
+  __syncthreads();
+  if (tid == 0) { a.gridbar[0] = 0u; a.gridbar[1] = 0u; a.gridbar[2] = 0u; }   // every CTA has arrived at both barriers
+}
+
 template <bool TRAIN>
 __global__ void __launch_bounds__(NT, 1) k_sgnn(const __grid_constant__ StepArgs a) {
   extern __shared__ __align__(16) float smem[];
@@ -1929,7 +2174,10 @@ __global__ void __launch_bounds__(NT, 1) k_sgnn(const __grid_constant__ StepArgs
   }
   if (a.stamps && threadIdx.x == 0 && blockIdx.x < 160) a.stamps[64 + blockIdx.x] = clock64() - t_cta0;           // CTA busy time
   if constexpr (TRAIN) {
-    if (a.fuse_tail) fused_tail(a, smem, stage_bits);
+    if (a.fuse_tail) {
+      if (a.world > 1) fused_tail_peers(a, smem, stage_bits);
+      else fused_tail(a, smem, stage_bits);
+    }
   }
 }
 

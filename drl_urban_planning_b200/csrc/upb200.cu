@@ -39,6 +39,12 @@ struct upb_ctx {
   long long* stamps = nullptr;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
   size_t prof_used = 0;
+  // multi-GPU fused step (upb_peer_export / upb_peer_connect)
+  float* xchg = nullptr;             // this rank's exchange buffer: [2][G_ROW] sums + [2][2][MAX_PEERS] flags | stage bits
+  int world = 1, rank = 0;
+  unsigned int peer_seq = 0;
+  std::vector<void*> peer_ptrs;      // host copy: exchange buffers of all ranks (own at [rank])
+  float** peers_dev = nullptr;       // device array of the same
 };
 
 namespace {
@@ -190,6 +196,10 @@ extern "C" void upb_destroy(upb_ctx* ctx) {
   cudaFree(ctx->steps);
   cudaFree(ctx->ticket);
   cudaFree(ctx->gridbar);
+  for (int p = 0; p < (int)ctx->peer_ptrs.size(); ++p)
+    if (p != ctx->rank && ctx->peer_ptrs[p]) cudaIpcCloseMemHandle(ctx->peer_ptrs[p]);
+  cudaFree(ctx->peers_dev);
+  cudaFree(ctx->xchg);
   if (ctx->host_pinned) cudaFreeHost(ctx->host_pinned);
   for (auto& ev : ctx->prof_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
   delete ctx;
@@ -274,7 +284,11 @@ extern "C" int upb_ppo_step(upb_ctx* ctx, const void* blob_dev, const int32_t* i
   if (int rc = check_ctx(ctx, "ppo_step")) return rc;
   const bool clip_now = ctx->cfg.clip_mode == UPB_CLIP_ALWAYS ||
                         (ctx->cfg.clip_mode == UPB_CLIP_REFERENCE && ctx->host_steps == 0);
-  if (clip_now || !ctx->coop || count <= 0) {      // clipping needs a grid-wide norm first: use the two-call path
+  if (ctx->world > 1) {
+    if (clip_now || !ctx->coop)
+      return set_error(UPB_ERR_ARG, "ppo_step: peers are connected and this step clips gradients; use upb_ppo_grad + "
+                                    "all-reduce + upb_apply for it (upb_next_step_fused() == 0)");
+  } else if (clip_now || !ctx->coop || count <= 0) {      // clipping needs a grid-wide norm first: use the two-call path
     int rc = upb_ppo_grad(ctx, blob_dev, ids, count, params, actions, advantages, returns, fixed_log_probs, exps,
                           inv_batch, inv_ind, grad_out, stream);
     if (rc != UPB_OK) return rc;
@@ -303,7 +317,11 @@ extern "C" int upb_ppo_step(upb_ctx* ctx, const void* blob_dev, const int32_t* i
   a.beta1 = ctx->cfg.beta1;
   a.beta2 = ctx->cfg.beta2;
   a.adam_eps = ctx->cfg.adam_eps;
-  const int grid = count < ctx->grid ? count : ctx->grid;
+  a.world = ctx->world;
+  a.rank = ctx->rank;
+  a.seq = ctx->world > 1 ? ++ctx->peer_seq : 0u;
+  a.peers = ctx->peers_dev;
+  const int grid = count < 1 ? 1 : (count < ctx->grid ? count : ctx->grid);     // an empty shard still takes part in the exchange
   void* kargs[] = {&a};
   const bool prof = prof_begin(ctx, s);
   UPB_CUDA(cudaLaunchCooperativeKernel((void*)k_sgnn<true>, dim3(grid), dim3(NT), kargs, SMEM_BYTES, s));
@@ -312,6 +330,62 @@ extern "C" int upb_ppo_step(upb_ctx* ctx, const void* blob_dev, const int32_t* i
   ctx->steps_cur = 1 - ctx->steps_cur;
   ctx->host_steps += 1;
   return UPB_OK;
+}
+
+// ---- multi-GPU fused step: exchange buffers shared between the ranks' processes with CUDA IPC ---------------------------
+static_assert(sizeof(cudaIpcMemHandle_t) == UPB_PEER_HANDLE_BYTES, "IPC handle size");
+
+extern "C" int upb_peer_export(upb_ctx* ctx, void* handle_out) {
+  if (int rc = check_ctx(ctx, "peer_export")) return rc;
+  if (!handle_out) return set_error(UPB_ERR_ARG, "peer_export: handle_out is null");
+  if (!ctx->xchg) {
+    const size_t bytes = sizeof(float) * 2 * G_ROW + sizeof(unsigned int) * 4 * MAX_PEERS;
+    UPB_CUDA(cudaMalloc(&ctx->xchg, bytes));
+    UPB_CUDA(cudaMemset(ctx->xchg, 0, bytes));
+    UPB_CUDA(cudaDeviceSynchronize());
+  }
+  cudaIpcMemHandle_t h;
+  UPB_CUDA(cudaIpcGetMemHandle(&h, ctx->xchg));
+  memcpy(handle_out, &h, sizeof(h));
+  return UPB_OK;
+}
+
+extern "C" int upb_peer_connect(upb_ctx* ctx, int world, int rank, const void* handles) {
+  if (int rc = check_ctx(ctx, "peer_connect")) return rc;
+  if (world < 2 || world > MAX_PEERS || rank < 0 || rank >= world || !handles)
+    return set_error(UPB_ERR_ARG, "peer_connect: need 2 <= world <= 16, 0 <= rank < world and world handles");
+  if (!ctx->xchg) return set_error(UPB_ERR_ARG, "peer_connect: call upb_peer_export first");
+  if (!ctx->peer_ptrs.empty()) return set_error(UPB_ERR_ARG, "peer_connect: already connected");
+  if (!ctx->coop) return set_error(UPB_ERR_CUDA, "peer_connect: cooperative launch is not supported on this device");
+  std::vector<void*> ptrs(world, nullptr);
+  for (int p = 0; p < world; ++p) {
+    if (p == rank) { ptrs[p] = ctx->xchg; continue; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, (const char*)handles + (size_t)p * sizeof(h), sizeof(h));
+    cudaError_t err = cudaIpcOpenMemHandle(&ptrs[p], h, cudaIpcMemLazyEnablePeerAccess);
+    if (err != cudaSuccess) {
+      for (int q = 0; q < p; ++q)
+        if (q != rank && ptrs[q]) cudaIpcCloseMemHandle(ptrs[q]);
+      char buf[256];
+      snprintf(buf, sizeof(buf), "peer_connect: cudaIpcOpenMemHandle(rank %d) failed: %s", p, cudaGetErrorString(err));
+      cudaGetLastError();
+      return set_error(UPB_ERR_CUDA, buf);
+    }
+  }
+  UPB_CUDA(cudaMalloc(&ctx->peers_dev, sizeof(float*) * world));
+  UPB_CUDA(cudaMemcpy(ctx->peers_dev, ptrs.data(), sizeof(float*) * world, cudaMemcpyHostToDevice));
+  ctx->peer_ptrs = ptrs;
+  ctx->world = world;
+  ctx->rank = rank;
+  ctx->peer_seq = 0;
+  return UPB_OK;
+}
+
+extern "C" int upb_next_step_fused(upb_ctx* ctx) {
+  if (!ctx) return 0;
+  const bool clip_now = ctx->cfg.clip_mode == UPB_CLIP_ALWAYS ||
+                        (ctx->cfg.clip_mode == UPB_CLIP_REFERENCE && ctx->host_steps == 0);
+  return (!clip_now && ctx->coop) ? 1 : 0;
 }
 
 extern "C" int upb_read_losses(upb_ctx* ctx, const float* grad, float* out4_host, void* stream) {

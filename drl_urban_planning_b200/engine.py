@@ -42,6 +42,7 @@ class Engine:
         with torch.cuda.device(self.device):
             _lib.check(_lib.lib().upb_create(C.byref(cfg), C.byref(self._ctx)), "upb_create")
         self.n_cap, self.e_cap = n_cap, e_cap
+        self.peers, self.peers_ok = 1, False          # multi-GPU fused step: see connect_peers
 
     def close(self):
         if getattr(self, "_ctx", None) is not None and self._ctx.value:
@@ -121,6 +122,46 @@ class Engine:
             _f32(exps, dev).data_ptr(), float(inv_batch), float(inv_ind), out.data_ptr(), self._stream()),
             "upb_ppo_step")
         return out
+
+    # ---- multi-GPU fused step (include/upb200.h: upb_peer_*) -----------------------------------------------------
+    def peer_export(self) -> bytes:
+        buf = C.create_string_buffer(_lib.UPB_PEER_HANDLE_BYTES)
+        _lib.check(_lib.lib().upb_peer_export(self._ctx, buf), "upb_peer_export")
+        return buf.raw
+
+    def peer_connect(self, world: int, rank: int, handles: bytes) -> None:
+        assert len(handles) == world * _lib.UPB_PEER_HANDLE_BYTES
+        _lib.check(_lib.lib().upb_peer_connect(self._ctx, int(world), int(rank), C.c_char_p(handles)), "upb_peer_connect")
+        self.peers = world
+
+    def next_step_fused(self) -> bool:
+        return bool(_lib.lib().upb_next_step_fused(self._ctx))
+
+    def connect_peers(self, process_group=None) -> bool:
+        """Exchange the ranks' IPC handles over `process_group` (NCCL) and map the peers' exchange buffers.  Collective;
+        returns True on every rank or False on every rank (then the NCCL all-reduce path stays in use)."""
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(process_group), dist.get_rank(process_group)
+        if world < 2 or getattr(self, "peers", 1) > 1:
+            return getattr(self, "peers", 1) > 1
+        ok = torch.ones(1, dtype=torch.int32, device=self.device)
+        try:
+            mine = torch.frombuffer(bytearray(self.peer_export()), dtype=torch.uint8).to(self.device)
+        except _lib.UpbError:
+            mine = torch.zeros(_lib.UPB_PEER_HANDLE_BYTES, dtype=torch.uint8, device=self.device)
+            ok.zero_()
+        everyone = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(everyone, mine, group=process_group)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=process_group)
+        if int(ok.item()) == 1:
+            try:
+                self.peer_connect(world, rank, b"".join(bytes(t.cpu().numpy().tobytes()) for t in everyone))
+            except _lib.UpbError:
+                ok.zero_()
+        # a rank that failed to map a peer must not leave the others waiting for it inside a kernel
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=process_group)
+        self.peers_ok = int(ok.item()) == 1
+        return self.peers_ok
 
     def apply(self, params: torch.Tensor, grad: torch.Tensor) -> None:
         _lib.check(_lib.lib().upb_apply(self._ctx, params.data_ptr(), grad.data_ptr(), self._stream()), "upb_apply")

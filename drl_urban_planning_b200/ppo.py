@@ -11,9 +11,11 @@ scalars per minibatch -- but a different data path:
   * one encoder pass yields value, log-prob and entropy (the reference runs the encoder twice per step);
   * loss scalars stay on the device and are read back once per epoch (the reference syncs 4x per step).
 
-Data parallel: every rank holds the whole buffer, takes `perm[i*B:(i+1)*B][rank::world]` of each global minibatch and
-all-reduces one 55 KB gradient+statistics buffer (NCCL sum) per step; 1/B and 1/|ind| are global, so the summed
-shard gradients equal the single-GPU batch gradient.
+Data parallel: every rank holds the whole buffer and takes `perm[i*B:(i+1)*B][rank::world]` of each global minibatch;
+1/B and 1/|ind| are global, so the summed shard gradients equal the single-GPU batch gradient (SURVEY.md section
+8(e)).  The per-rank 58 KB column sums are exchanged inside the step kernel through peer memory (NVLink, no NCCL call,
+one launch per step); steps that clip gradients, and process groups without peer access, all-reduce one 55 KB
+gradient+statistics buffer with NCCL instead.
 """
 from __future__ import annotations
 
@@ -32,7 +34,8 @@ class PPOUpdater:
     def __init__(self, flat_params, n_cap: int, e_cap: int, device, lr: float = 4e-4, eps: float = 1e-5,
                  clip_epsilon: float = 0.2, value_pred_coef: float = 0.5, entropy_coef: float = 0.01,
                  gamma: float = 1.0, tau: float = 0.0, opt_num_epochs: int = 4, mini_batch_size: int = 256,
-                 clip_mode: int = _lib.CLIP_REFERENCE, process_group="auto", pack_threads: int = 0):
+                 clip_mode: int = _lib.CLIP_REFERENCE, process_group="auto", pack_threads: int = 0,
+                 use_peers: bool = True):
         self.device = torch.device(device)
         self.engine = Engine(self.device, n_cap, e_cap, lr=lr, eps=eps, clip_epsilon=clip_epsilon,
                              value_pred_coef=value_pred_coef, entropy_coef=entropy_coef, clip_mode=clip_mode)
@@ -60,6 +63,13 @@ class PPOUpdater:
             self.world = dist.get_world_size(process_group)
             self.rank = dist.get_rank(process_group)
         self.grad = self.engine.new_grad_buffer()
+        # ranks on one node exchange gradients inside the step kernel (peer memory over NVLink) when the process group
+        # is NCCL and the peers' buffers can be mapped; otherwise one NCCL all-reduce per step
+        self.fused_exchange = False
+        if use_dist and use_peers and self.world > 1:
+            import torch.distributed as dist
+            if dist.get_backend(process_group) == "nccl":
+                self.fused_exchange = self.engine.connect_peers(process_group)
         self.blob: Optional[PackedGraphs] = None
         self._dev_blob_buf = None
         self.loss_iter = 0
@@ -94,8 +104,9 @@ class PPOUpdater:
         graphs, `global_ind` of which have exps != 0): urban_planning_agent.py:322-337."""
         args = (self.blob, self.params, self.actions, self.advantages, self.returns, self.fixed_log_probs, self.exps,
                 1.0 / max(global_batch, 1), 1.0 / max(global_ind, 1))
-        if self.world == 1:
-            self.engine.ppo_step(*args, ids=ids, out=self.grad)          # one launch: gradient, reduction, Adam
+        if self.world == 1 or (self.fused_exchange and self.engine.next_step_fused()):
+            # one launch: gradient, reduction (over the ranks too, through peer memory), Adam
+            self.engine.ppo_step(*args, ids=ids, out=self.grad)
         else:
             self.engine.ppo_grad(*args, ids=ids, out=self.grad)
             self.allreduce(self.grad)

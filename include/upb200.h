@@ -136,6 +136,21 @@ int upb_ppo_step(upb_ctx* ctx, const void* blob_dev, const int32_t* ids, int cou
                  const float* fixed_log_probs, const float* exps, float inv_batch, float inv_ind,
                  float* grad_out, void* stream);
 
+/* ---- multi-GPU fused step (one process per GPU, peers on one node reachable over NVLink / NVSwitch or PCIe P2P) ----
+ * The reference is single-process; data parallelism over the graphs of a minibatch is this library's extension
+ * (SURVEY.md section 8e).  Without these calls the ranks exchange upb_ppo_grad's 55 KB buffer with ncclAllReduce and
+ * call upb_apply.  With them the exchange happens inside upb_ppo_step's kernel through peer memory:
+ *   upb_peer_export   writes UPB_PEER_HANDLE_BYTES bytes (a CUDA IPC handle of this context's exchange buffer);
+ *   upb_peer_connect  takes the `world` handles gathered from all ranks in rank order and maps the peers' buffers;
+ *                     afterwards every rank must call upb_ppo_step the same number of times (empty shards included);
+ *   upb_next_step_fused  1 if the next optimiser step can run as upb_ppo_step (no gradient clipping on it), else 0:
+ *                     a clipping step needs the global norm first and takes upb_ppo_grad + all-reduce + upb_apply.
+ * All ranks sum the per-rank gradients in rank order, so their parameters stay bit-identical. */
+#define UPB_PEER_HANDLE_BYTES 64
+int upb_peer_export(upb_ctx* ctx, void* handle_out);
+int upb_peer_connect(upb_ctx* ctx, int world, int rank, const void* handles);
+int upb_next_step_fused(upb_ctx* ctx);
+
 /* the 4 scalars the reference logs per minibatch (urban_planning_agent.py:338-345), from a gradient buffer:
  * out4 = {loss, value_loss, surr_loss, entropy_loss}.  Synchronises `stream`. */
 int upb_read_losses(upb_ctx* ctx, const float* grad, float* out4_host, void* stream);
