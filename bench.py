@@ -268,6 +268,7 @@ def main():
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     total_ms = float(ms.item())
     launches = eng.launches - launches0
+    losses = eng.read_losses(grad)          # of the last timed step
     # the timed region lasts a few ms, too short for nvidia-smi: keep the same load for ~1 s more (same count on every
     # rank) so the clock / throttle record describes this workload
     for i in range(int(min(20000, max(0.0, 1000.0 / max(total_ms / args.steps, 1e-3))))):
@@ -275,7 +276,6 @@ def main():
     torch.cuda.synchronize()
     clk = clocks.stop() if rank == 0 else None
     value = BATCH * world * args.steps / (total_ms * 1e-3)
-    losses = eng.read_losses(grad)
     assert all(np.isfinite(losses)), losses
 
     # ---- roofline of the dominant kernel (fused SGNN fwd+bwd), CUDA events on the launching stream
