@@ -199,6 +199,9 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    # host side of the end-to-end path: this rank's packer threads and pinned staging buffers on the GPU's NUMA node
+    from drl_urban_planning_b200.engine import bind_host_to_gpu_node
+    numa = bind_host_to_gpu_node(dev)
 
     # ---- workload: resident pool of minibatches, larger than L2
     t0 = time.time()
@@ -317,7 +320,8 @@ def main():
         h2d = 0
         # the ranks of one node share its host cores: each packer gets its share (0 = all CPUs of this process, <= 32)
         local_world = int(os.environ.get("LOCAL_WORLD_SIZE", world))
-        pack_threads = 0 if local_world <= 1 else max(2, min(32, len(os.sched_getaffinity(0)) // local_world))
+        sharers = local_world if numa is None else -(-local_world // numa[2])       # ranks that share these CPUs
+        pack_threads = 0 if sharers <= 1 else max(2, min(32, len(os.sched_getaffinity(0)) // sharers))
         pool_ex = ThreadPoolExecutor(1)
 
         def pack_job(i):
@@ -412,6 +416,7 @@ def main():
                          "kernel_share_of_step": k_avg_ms / (total_ms / args.steps)},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
             "losses_last_step": [float(x) for x in losses], "setup_s": setup_s,
+            "host_numa": None if numa is None else {"node": numa[0], "cpus": len(numa[1])},
         }
         print(json.dumps(out), flush=True)
     if world > 1:

@@ -26,6 +26,42 @@ def _f32(t: torch.Tensor, device) -> torch.Tensor:
     return t
 
 
+def _cpulist(text: str):
+    out = []
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        a, _, b = part.partition("-")
+        out += list(range(int(a), int(b or a) + 1))
+    return out
+
+
+def bind_host_to_gpu_node(device=None):
+    """Restrict this process (and the threads it creates later: the packer's workers, the pinned-buffer first touch) to
+    the CPUs of the NUMA node the GPU hangs off.  Host glue for the end-to-end path: the packer reads rollout states
+    and writes the pinned staging blob, the copy engine reads it; all three want the same node.  Returns
+    (node, cpus, nodes_total) or None when the topology cannot be read (then nothing is changed).  Call it before the
+    big host allocations; one process per GPU."""
+    import glob
+    import os
+    try:
+        idx = torch.cuda.current_device() if device is None else torch.device(device).index or 0
+        pr = torch.cuda.get_device_properties(idx)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read().strip())
+        nodes = len(glob.glob("/sys/devices/system/node/node[0-9]*"))
+        if node < 0 or nodes < 2:
+            return None
+        cpus = set(_cpulist(open(f"/sys/devices/system/node/node{node}/cpulist").read()))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if len(allowed) < 2:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node, sorted(allowed), nodes
+    except (OSError, ValueError, AttributeError, RuntimeError):
+        return None
+
+
 class Engine:
     def __init__(self, device, n_cap: int, e_cap: int, lr: float = 4e-4, betas=(0.9, 0.999), eps: float = 1e-5,
                  clip_epsilon: float = 0.2, value_pred_coef: float = 0.5, entropy_coef: float = 0.01,
