@@ -59,6 +59,7 @@ _PROTOS = {
     "upb_grid_size": (C.c_int, [_VP]),
     "upb_set_stamp_buffer": (C.c_int, [_VP, _VP]),
     "upb_launch_count": (C.c_int64, [_VP]),
+    "upb_select_action": (C.c_int, [_VP, _VP, _VP, C.c_int, _VP, _VP, _VP, _VP]),
     "upb_peer_export": (C.c_int, [_VP, _VP]),
     "upb_peer_connect": (C.c_int, [_VP, C.c_int, C.c_int, _VP]),
     "upb_next_step_fused": (C.c_int, [_VP]),

@@ -76,6 +76,15 @@ class B200Update:
         ref = self.agent.actor_critic_net.state_dict()
         self.agent.actor_critic_net.load_state_dict({k: torch.as_tensor(v).to(ref[k].device) for k, v in sd.items()})
 
+    # ---- optimiser state.  The reference's checkpoints hold no Adam state (save_checkpoint :172-193): a
+    # resumed run restarts the moments, and so does a fresh B200Update.  These two calls let a caller keep them.
+    def optimizer_state(self) -> dict:
+        m, v, steps = self.updater.engine.get_opt_state()
+        return {"exp_avg": m, "exp_avg_sq": v, "steps": steps}
+
+    def load_optimizer_state(self, state: dict) -> None:
+        self.updater.engine.set_opt_state(state["exp_avg"], state["exp_avg_sq"], state["steps"])
+
     def update_params(self, batch, iteration):
         """Signature and effects of UrbanPlanningAgent.update_params (:248-271)."""
         t0 = time.time()

@@ -172,6 +172,8 @@ struct StepArgs {
   float* out_logp;
   float* out_entropy;
   int* out_greedy;
+  const float* uniforms;   // optional [blob count]: one uniform in [0, 1) per graph -> out_sample (forward kernel only)
+  int* out_sample;         // action index drawn by inverse CDF over the candidates in index order
   float* gpart;        // [gridDim.x][G_ROW]
   float* scratch;      // [gridDim.x][scratch_stride]
   size_t scratch_stride;
@@ -1073,6 +1075,38 @@ __device__ __forceinline__ void softmax_seeds(const StepArgs& a, const BlobHeade
     if (a.out_logp) a.out_logp[gid] = logp;
     if (a.out_entropy) a.out_entropy[gid] = H;
     if (a.out_greedy) a.out_greedy[gid] = greedy;
+  }
+  if constexpr (!TRAIN) {
+    // Sampled action (policy.py:81-83 `dist.sample()`), from a caller-supplied uniform: the first candidate, in index
+    // order, whose cumulative probability reaches u.  (torch's sampler consumes its generator differently, so sampled
+    // rollouts are reproducible per uniform stream, not bit-equal to Categorical.sample.)
+    if (a.uniforms != nullptr && a.out_sample != nullptr) {
+      const float u = a.uniforms[gid];
+      int pick = -1;
+      if (k > 0) {
+        const float target = u * warp_sum(lsum);
+        float run = 0.f;
+        for (int base = 0; base < k && pick < 0; base += 32) {
+          const int j = base + lane;
+          float c = j < k ? expf(g.z[j] - zmax) : 0.f;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const float t = __shfl_up_sync(0xffffffffu, c, o);
+            if (lane >= o) c += t;
+          }
+          c += run;
+          const unsigned hit = __ballot_sync(0xffffffffu, j < k && c >= target);
+          if (hit) pick = base + __ffs(hit) - 1;
+          run = __shfl_sync(0xffffffffu, c, 31);
+        }
+        if (pick < 0) pick = k - 1;                       // u * sum rounded above the last partial sum
+        pick = g.cidx[pick];
+      } else {                                            // empty mask: uniform over the padded width
+        const int cap = g.stage == 0 ? hd.e_cap : hd.n_cap;
+        pick = min(cap - 1, max(0, (int)(u * (float)cap)));
+      }
+      if (lane == 0) a.out_sample[gid] = pick;
+    }
   }
   if constexpr (TRAIN) {
     const float R = sc[SC_RET], dv = V - R;

@@ -225,6 +225,21 @@ extern "C" int upb_forward(upb_ctx* ctx, const void* blob_dev, const int32_t* id
   return UPB_OK;
 }
 
+extern "C" int upb_select_action(upb_ctx* ctx, const void* blob_dev, const int32_t* ids, int count, const float* params,
+                                 const float* uniforms, int32_t* action_index, void* stream) {
+  if (int rc = check_ctx(ctx, "select_action")) return rc;
+  if (!blob_dev || !params || !action_index || count < 0) return set_error(UPB_ERR_ARG, "select_action: bad argument");
+  if (count == 0) return UPB_OK;
+  StepArgs a = base_args(ctx, blob_dev, ids, count, params, nullptr);
+  if (uniforms) { a.uniforms = uniforms; a.out_sample = action_index; }
+  else a.out_greedy = action_index;
+  const int grid = count < ctx->grid ? count : ctx->grid;
+  k_sgnn<false><<<grid, NT, SMEM_BYTES, (cudaStream_t)stream>>>(a);
+  ctx->launches += 1;
+  UPB_CUDA(cudaGetLastError());
+  return UPB_OK;
+}
+
 extern "C" int upb_ppo_grad(upb_ctx* ctx, const void* blob_dev, const int32_t* ids, int count, const float* params,
                             const float* actions, const float* advantages, const float* returns,
                             const float* fixed_log_probs, const float* exps, float inv_batch, float inv_ind,

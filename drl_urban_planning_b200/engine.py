@@ -159,6 +159,23 @@ class Engine:
             "upb_ppo_step")
         return out
 
+    def select_action(self, blob: PackedGraphs, params: torch.Tensor, uniforms: Optional[torch.Tensor] = None,
+                      ids: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Action index per graph of the blob (int32, indexed by blob position): greedy arg-max when `uniforms` is
+        None (policy.py:72-79 `mean_action`), else drawn by inverse CDF from one uniform per graph (policy.py:81-83)."""
+        self._check_blob(blob)
+        out = torch.zeros(blob.count, dtype=torch.int32, device=self.device)
+        cnt = blob.count if ids is None else int(ids.numel())
+        u = None
+        if uniforms is not None:
+            u = _f32(uniforms, self.device).reshape(-1)
+            if u.numel() != blob.count:
+                raise ValueError("uniforms must hold one value per graph of the blob")
+        _lib.check(_lib.lib().upb_select_action(self._ctx, blob.dev_ptr(), _ptr(ids), cnt, params.data_ptr(),
+                                                None if u is None else u.data_ptr(), out.data_ptr(), self._stream()),
+                   "upb_select_action")
+        return out
+
     # ---- multi-GPU fused step (include/upb200.h: upb_peer_*) -----------------------------------------------------
     def peer_export(self) -> bytes:
         buf = C.create_string_buffer(_lib.UPB_PEER_HANDLE_BYTES)

@@ -145,6 +145,15 @@ class _EngineMixin:
         blob = pack_states(x, self.shared_net.max_num_nodes, self.shared_net.max_num_edges).to(device)
         return eng.forward(blob, self._flat_params(device), actions, want_greedy=want_greedy)
 
+    def _cuda_sample(self, x, uniforms=None):
+        from .packing import pack_states
+        device = next(self.parameters()).device
+        eng = self._engine(device)
+        blob = pack_states(x, self.shared_net.max_num_nodes, self.shared_net.max_num_edges).to(device)
+        if uniforms is None:
+            uniforms = torch.rand(len(x), device=device)
+        return eng.select_action(blob, self._flat_params(device), uniforms=uniforms)
+
 
 class UrbanPlanningPolicy(nn.Module, _EngineMixin):
     """reference models/policy.py:5-104."""
@@ -188,12 +197,15 @@ class UrbanPlanningPolicy(nn.Module, _EngineMixin):
         d1 = torch.distributions.Categorical(logits=torch.stack(rd)) if rd else None
         return d0, d1, stage
 
-    def select_action(self, x, mean_action=False):
-        """(B, 2) float32: column 0 land-use edge index, column 1 road node index (policy.py:67-85)."""
+    def select_action(self, x, mean_action=False, uniforms=None):
+        """(B, 2) float32: column 0 land-use edge index, column 1 road node index (policy.py:67-85).
+        On CUDA a batch of states is evaluated by the fused forward kernel: greedy arg-max (bit-exact), or, for
+        mean_action=False, inverse-CDF sampling from `uniforms` (B values in [0,1); torch.rand on the device if None)."""
         if next(self.parameters()).is_cuda:
-            if not mean_action:
-                raise NotImplementedError("sampled actions are drawn on the CPU rollout path; CUDA offers greedy")
-            _, _, _, greedy = self._cuda_forward(x, want_greedy=True)
+            if mean_action:
+                _, _, _, greedy = self._cuda_forward(x, want_greedy=True)
+            else:
+                greedy = self._cuda_sample(x, uniforms)
             stage = np.stack([np.asarray(s[8].detach().cpu() if hasattr(s[8], "detach") else s[8]) for s in x])
             out = torch.zeros(len(x), 2, dtype=self.agent.dtype, device=greedy.device)
             sid = torch.as_tensor(stage[:, :2].argmax(1), device=greedy.device)

@@ -112,6 +112,17 @@ int upb_forward(upb_ctx* ctx, const void* blob_dev, const int32_t* ids, int coun
                 const float* actions, float* value, float* log_prob, float* entropy, int32_t* greedy,
                 void* stream);
 
+/* UrbanPlanningPolicy.select_action (urban_planning/models/policy.py:67-85) for a batch of packed graphs:
+ * action_index[g] (indexed by blob position, like upb_forward's outputs) = index of the chosen land-use edge (stage 0
+ * graphs) or road node (stage 1 graphs).
+ *   uniforms == NULL : mean_action=True, `probs.argmax` with the first-index tie break (bit-exact);
+ *   uniforms != NULL : mean_action=False, f32[blob count] uniforms in [0,1), one per graph; the action is the first
+ *                      mask-true index whose cumulative probability reaches u (inverse CDF in index order).  torch's
+ *                      Categorical.sample consumes its generator differently: sampled rollouts are reproducible per
+ *                      uniform stream, not bit-equal to the reference's draws. */
+int upb_select_action(upb_ctx* ctx, const void* blob_dev, const int32_t* ids, int count, const float* params,
+                      const float* uniforms, int32_t* action_index, void* stream);
+
 /* Forward + backward of one (shard of a) minibatch: value_loss + ppo_entropy_loss + loss.backward()
  * (urban_planning_agent.py:330-335, khrylib/rl/agents/agent_pg.py:19-23).  inv_batch = 1/B and
  * inv_ind = 1/|ind| are those of the GLOBAL minibatch, so shards on several GPUs sum to the exact batch

@@ -335,3 +335,39 @@ def test_fused_step_matches_two_call_path(dev):
         assert e1.get_opt_state()[2].tolist() == e2.get_opt_state()[2].tolist()
         m1, v1, _ = e1.get_opt_state(); m2, v2, _ = e2.get_opt_state()
         assert rel(m2, m1) < 1e-5 and rel(v2, v1) < 1e-5
+
+
+def test_select_action_greedy_and_sampled(dev):
+    """upb_select_action (policy.py:67-85): greedy = the forward kernel's arg-max (bit-exact); sampled = inverse CDF of
+    the float64 oracle's candidate probabilities at the supplied uniform (the index must bracket u up to fp32 rounding
+    of the cumulative sums), including u = 0, u -> 1 and an empty action mask."""
+    states, actions = synth.make_states(21, "small", 40)
+    states[3][6][:] = False; states[3][7][:] = False                      # empty mask: uniform over the padded width
+    flat = PL.default_init(21)
+    blob = pack_states(states).to(dev)
+    eng = make_engine(dev, blob.n_cap, blob.e_cap)
+    params = t(flat, dev)
+    _, _, _, greedy = eng.forward(blob, params, t(actions, dev), want_greedy=True)
+    assert torch.equal(eng.select_action(blob, params), greedy.to(torch.int32))
+    rng = np.random.default_rng(5)
+    u = rng.random(len(states)).astype(np.float32)
+    u[0], u[1] = 0.0, np.float32(1.0 - 2.0 ** -24)
+    picked = eng.select_action(blob, params, uniforms=t(u, dev)).cpu().numpy()
+    P = ON._p64(flat)
+    for i, st in enumerate(states):
+        g = ON.unpad(st)
+        c = ON.forward(P, g, keep=True)["cache"]
+        idx, p = c["idx"], c["p"]
+        if idx.size == 0:
+            cap = blob.e_cap if st[8][0] > 0 else blob.n_cap
+            assert picked[i] == min(cap - 1, int(u[i] * cap))
+            continue
+        assert picked[i] in idx, i
+        j = int(np.flatnonzero(idx == picked[i])[0])
+        cdf = np.cumsum(p)
+        lo = cdf[j - 1] if j > 0 else 0.0
+        assert lo - 1e-5 <= float(u[i]) <= cdf[j] + 1e-5, (i, j, lo, float(u[i]), cdf[j])
+    # a subset through an index list leaves the other slots untouched (zero-initialised output)
+    ids = torch.as_tensor(np.array([5, 7, 11], np.int32), device=dev)
+    part = eng.select_action(blob, params, uniforms=t(u, dev), ids=ids).cpu().numpy()
+    assert np.array_equal(part[[5, 7, 11]], picked[[5, 7, 11]]) and part[[0, 1, 2]].tolist() == [0, 0, 0]
