@@ -46,3 +46,12 @@ def test_errors_are_reported_not_thrown():
     n = C.c_uint64()
     rc = L.upb_pack_measure(1, None, 10, 10, 1, C.byref(n))
     assert rc != 0 and b"pack" in L.upb_last_error()
+
+
+def test_cpulist_parser_of_the_numa_helper():
+    from drl_urban_planning_b200.engine import _cpulist, bind_host_to_gpu_node
+    assert _cpulist("0-3,8,10-11\n") == [0, 1, 2, 3, 8, 10, 11]
+    assert _cpulist("") == []
+    import torch
+    if not torch.cuda.is_available():
+        assert bind_host_to_gpu_node(0) is None      # no GPU topology to read: nothing is changed
