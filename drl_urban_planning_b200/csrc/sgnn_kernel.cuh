@@ -827,14 +827,21 @@ __device__ __forceinline__ void group_bar(int id, int nthreads) {      // named 
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-// numeric feature encoder (state_encoder.py:35-57,187).  Layer 0: warps 0,1 (one hidden unit per lane).
-__device__ __forceinline__ void numeric_l0(const float* vn, const float* x52, float* a0, int warp, int lane) {
-  const int u = warp * 32 + lane;
+// numeric feature encoder (state_encoder.py:35-57,187).  Layer 0: all 512 threads, 8 lanes per hidden unit (the two
+// warps that used to own it were 1.5 k cycles late at the next barrier).
+__device__ __forceinline__ void numeric_l0(const float* vn, const float* x52, float* a0, int tid) {
+  const int u = tid >> 3, p = tid & 7;
   const float* w = vn + VN_NW0 + u * 53;
-  float s0 = vn[VN_NB0 + u], s1 = 0.f;
-#pragma unroll 13
-  for (int k = 0; k < NUMD; k += 2) { s0 = fmaf(w[k], x52[k], s0); s1 = fmaf(w[k + 1], x52[k + 1], s1); }
-  a0[u] = tanhf(s0 + s1);
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < 7; ++k) {
+    const int c = p + 8 * k;
+    if (c < NUMD) s = fmaf(w[c], x52[c], s);
+  }
+  s += __shfl_xor_sync(0xffffffffu, s, 1);
+  s += __shfl_xor_sync(0xffffffffu, s, 2);
+  s += __shfl_xor_sync(0xffffffffu, s, 4);
+  if (p == 0) a0[u] = tanhf(s + vn[VN_NB0 + u]);
 }
 // Layer 1: one warp, 16 units x 2 halves of the 64 inputs
 __device__ __forceinline__ void numeric_l1(const float* vn, const float* a0, float* hnum, int lane) {
@@ -1243,7 +1250,7 @@ __device__ void graph_body(const StepArgs& a, const BlobHeader& hd, const GraphD
   UPB_STAMP(1);
 
   // ================================================================================ forward
-  if (warp < 2) numeric_l0(vn, sV + V_X52, sV + V_A0, warp, lane);   // numeric encoder, layer 0 (state_encoder.py:35-57)
+  numeric_l0(vn, sV + V_X52, sV + V_A0, tid);                        // numeric encoder, layer 0 (state_encoder.py:35-57)
   for (int i = tid; i < n; i += NT) g.inv[i] = 1.0f / ((float)(g.rp[i + 1] - g.rp[i]) + EPS_DEG);
   // h^0 = X We^T + be (state_encoder.py:189)
   if constexpr (BIG) {   // 4 lanes per node, 4 channels per lane, features from global memory

@@ -266,9 +266,10 @@ class Engine:
     @staticmethod
     def graph_cost(info: np.ndarray) -> np.ndarray:
         """Estimated cycles of one graph in the fused training kernel from (n, e, k, stage) rows
-        (fit to tools/phase_times.py: pulls ~ 22 / edge, node phases ~ 146 / node, head ~ 150 / candidate)."""
+        (least-squares fit of the per-CTA busy cycles, tools/balance_check.py: pulls ~ 17 / edge, node phases ~ 80 /
+        node, policy head ~ 134 / candidate, and ~ 41 k cycles per graph that do not depend on its size)."""
         i = np.asarray(info, dtype=np.int64)
-        return 22 * i[:, 1] + 146 * i[:, 0] + 150 * i[:, 2] + 15000
+        return 17 * i[:, 1] + 80 * i[:, 0] + 134 * i[:, 2] + 41500
 
     def balance_ids(self, ids: np.ndarray, cost: np.ndarray) -> np.ndarray:
         """Order graph ids for the kernel's static schedule (ids[i] -> CTA i % grid, round i // grid).

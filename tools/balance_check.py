@@ -31,6 +31,22 @@ A = np.stack([info[ids_np[:g], 1], info[ids_np[:g], 0], info[ids_np[:g], 2], np.
 single = ng == 1
 coef, *_ = np.linalg.lstsq(A[single], busy[single], rcond=None)
 print("fit on single-graph CTAs: cycles = %.1f e + %.1f n + %.1f k + %.0f" % tuple(coef))
+# all CTAs: features summed over the CTA's graphs (e, n, k of land-use graphs, k of road graphs, graph count)
+F = np.zeros((g, 5))
+for i, gid in enumerate(ids_np):
+    n_, e_, k_, st_ = info[gid]
+    F[i % g] += [e_, n_, k_ if st_ == 0 else 0, k_ if st_ == 1 else 0, 1]
+coef2, *_ = np.linalg.lstsq(F, busy.astype(float), rcond=None)
+res = busy - F @ coef2
+print("fit on all CTAs: cycles = %.1f e + %.1f n + %.1f k_landuse + %.1f k_road + %.0f per graph;  residual rms %.0f (%.1f%% of mean)"
+      % (*coef2, np.sqrt((res ** 2).mean()), 100 * np.sqrt((res ** 2).mean()) / busy.mean()))
+# what LPT would achieve with the refitted model (true cost taken as the fitted per-graph cost)
+true_cost = coef2[0] * info[:, 1] + coef2[1] * info[:, 0] + coef2[2] * info[:, 2] * (info[:, 3] == 0) + coef2[3] * info[:, 2] * (info[:, 3] == 1) + coef2[4]
+ids2 = eng.balance_ids(np.arange(count), true_cost)
+load = np.zeros(g)
+for i, gid in enumerate(ids2): load[i % g] += true_cost[gid]
+print("refitted model + LPT: predicted max %.0f mean %.0f (balance %.3f); current: measured max %d mean %.0f (balance %.3f)"
+      % (load.max(), load.mean(), load.mean() / load.max(), busy.max(), busy.mean(), busy.mean() / busy.max()))
 print("busy max %d mean %.0f; predicted max %.0f mean %.0f; corr %.3f" % (busy.max(), busy.mean(), pred.max(), pred.mean(), np.corrcoef(busy, pred)[0, 1]))
 top = np.argsort(-busy)[:5]
 for c in top:
