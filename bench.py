@@ -177,8 +177,6 @@ def main():
     ap.add_argument("--pool", type=int, default=16, help="minibatches resident in HBM (16 x 11.5 MB > 126 MB L2)")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
-    ap.add_argument("--steps-per-launch", type=int, default=10,
-                    help="optimiser steps per cooperative launch in the timed region (upb_ppo_steps); 1 = one launch per step")
     ap.add_argument("--nccl-exchange", action="store_true", help="multi-GPU: all-reduce the gradients with NCCL instead of the in-kernel peer exchange")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -253,34 +251,6 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # Several optimiser steps per cooperative launch (upb_ppo_steps), as PPOUpdater issues the steps of an epoch: the
-    # index lists of the timed steps are laid out in sequence before the clock starts (51 KB); the work per step is
-    # unchanged (parameters are updated and re-read between the steps).  --steps-per-launch 1 = one launch per step.
-    L = max(1, args.steps_per_launch)
-    multi = L > 1 and (world == 1 or fused_exchange)
-    if multi:
-        pool_ids = torch.stack(mb_ids)                                        # [pool, BATCH]
-        order = torch.as_tensor([(args.warmup + i) % args.pool for i in range(args.steps)], device=dev)
-        seq_ids = pool_ids[order].contiguous()                                # [steps, BATCH]
-        seq_counts = torch.full((args.steps,), BATCH, dtype=torch.int32, device=dev)
-        seq_scales = torch.tensor([[1.0 / gB, 1.0 / gI]] * args.steps, dtype=torch.float32, device=dev)
-        multi_out = torch.zeros(min(L, args.steps), _lib.UPB_GRAD_STRIDE, dtype=torch.float32, device=dev)
-
-    def run_timed_steps():
-        if not multi:
-            for i in range(args.steps):
-                step(args.warmup + i)
-            return None
-        i = 0
-        while i < args.steps:
-            k = min(L, args.steps - i)
-            if not eng.next_step_fused():       # a clipping step (never after the warm-up in CLIP_REFERENCE mode)
-                step(args.warmup + i); i += 1; continue
-            out = eng.ppo_steps(blob, params, act, adv, ret, fixed, exps, seq_ids[i:i + k], seq_counts[i:i + k],
-                                seq_scales[i:i + k], BATCH, out=multi_out)
-            i += k
-        return out[k - 1]                                                     # report of the last step
-
     for i in range(args.warmup):
         step(i)
     barrier()
@@ -292,7 +262,8 @@ def main():
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
-    last_report = run_timed_steps()
+    for i in range(args.steps):
+        step(args.warmup + i)
     ev1.record()
     barrier()
     ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
@@ -300,8 +271,6 @@ def main():
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     total_ms = float(ms.item())
     launches = eng.launches - launches0
-    if last_report is not None:
-        grad.copy_(last_report)
     losses = eng.read_losses(grad)          # of the last timed step
     # the timed region lasts a few ms, too short for nvidia-smi: keep the same load for ~1 s more (same count on every
     # rank) so the clock / throttle record describes this workload
@@ -437,7 +406,6 @@ def main():
             "config": {"workload": f"{args.community} (cfg {args.community}), PPO minibatch update, {BATCH} rollout graphs per GPU "
                                    f"per step, caps {blob.n_cap}/{blob.e_cap}, mean n={info[:, 0].mean():.0f} e={info[:, 1].mean():.0f}",
                        "global_batch": BATCH * world, "parallelism": f"dp{world}",
-                       "steps_per_launch": L if multi else 1,
                        "gradient_exchange": ("none (one GPU)" if world == 1 else
                                              "inside the step kernel, peer memory over NVLink" if fused_exchange else
                                              "ncclAllReduce of the 55 KB gradient buffer + upb_apply"),

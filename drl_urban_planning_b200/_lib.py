@@ -50,8 +50,6 @@ _PROTOS = {
     "upb_apply": (C.c_int, [_VP, _VP, _VP, _VP]),
     "upb_ppo_step": (C.c_int, [_VP, _VP, _VP, C.c_int, _VP, _VP, _VP, _VP, _VP, _VP, C.c_float, C.c_float,
                                _VP, _VP]),
-    "upb_ppo_steps": (C.c_int, [_VP, _VP, _VP, C.c_int, _VP, _VP, C.c_int, C.c_int, _VP, _VP, _VP, _VP, _VP, _VP, _VP,
-                                _VP]),
     "upb_read_losses": (C.c_int, [_VP, _VP, C.POINTER(C.c_float), _VP]),
     "upb_gae": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int, C.c_float, C.c_float, _VP, _VP, _VP]),
     "upb_get_opt_state": (C.c_int, [_VP, _VP, _VP, _VP]),

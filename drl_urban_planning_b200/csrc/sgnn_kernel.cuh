@@ -100,13 +100,11 @@ constexpr int V_TMP16B = 1816;  // [16]
 constexpr int V_SC = 1832;      // [24] scalars
 constexpr int V_WEFF = 1856;    // [32][16] Weff (land use), row-major copy for the head backward
 constexpr int V_TMP32 = 2368;   // [32] block-reduce results
-constexpr int V_STEP = 2400;    // [2] 1/B and 1/|ind| of the optimiser step being processed (+6 pad)
-constexpr int V_END = 2408;
+constexpr int V_END = 2400;
 // scalar slots
 constexpr int SC_VALUE = 0, SC_MAX = 1, SC_SUM = 2, SC_LSE = 3, SC_ENT = 4, SC_LOGP = 5, SC_GV = 6, SC_GLP = 7,
               SC_GH = 8, SC_Z = 9, SC_SLOT = 10, SC_BEST = 11, SC_GDOT = 12, SC_ACT = 13, SC_RET = 14, SC_EXP = 15,
               SC_FLP = 16, SC_ADV = 17, SC_QUEUE = 18;
-constexpr int SC_INVB = V_STEP - V_SC, SC_INVI = SC_INVB + 1;   // the step's 1/B and 1/|ind| seen from the scalar block
 
 constexpr int S_VEC = S_WEND;
 constexpr int S_RED = S_VEC + V_END;             // [NW][20] block-reduce scratch
@@ -183,19 +181,13 @@ struct StepArgs {
   // fused tail (single GPU, no clipping this step): cross-CTA gradient reduction + attention chain + Adam inside
   // the same launch, separated by grid barriers (cooperative launch: all CTAs are co-resident)
   int fuse_tail;
-  // several optimiser steps in one launch (upb_ppo_steps): step s uses ids + s * ids_stride, step_counts[s] graphs,
-  // step_scales[2 s] = 1/B and [2 s + 1] = 1/|ind|, writes grad_out + s * UPB_GRAD_STRIDE, and ends with a grid barrier
-  int num_steps;               // 0 / 1 = one step described by count, inv_batch, inv_ind
-  int ids_stride;
-  const int* step_counts;
-  const float* step_scales;
-  const long long* steps_base; // [2][4] ping-pong step counters; step s reads row (steps_cur + s) & 1, writes the other
-  int steps_cur;
   float* params_rw;            // == params, writable
   float* gsum;                 // [G_ROW]
   float* grad_out;             // [UPB_GRAD_STRIDE]
   float* adam_m;
   float* adam_v;
+  const long long* steps_in;   // [4]
+  long long* steps_out;        // [4]
   unsigned int* gridbar;       // [3] two arrival counters + stage bits, zero between launches
   float lr, beta1, beta2, adam_eps;
   // multi-GPU fused tail (upb_peer_connect): the per-rank column sums are exchanged through peer memory (NVLink) inside
@@ -406,24 +398,24 @@ __device__ __forceinline__ void load_weights(const float* __restrict__ P, float*
   static_assert(NT == 512, "load_weights is laid out for 512 threads");
   const int o = t >> 4, c = t & 15;
   const int src = o < 16 ? o * 32 + c : (o - 16) * 32 + 16 + c;          // (P | Q) split of a gcn weight row
-  const float wet = (t < 384 && (t >> 4) < F) ? __ldcg(P + P_ENC_W + c * F + (t >> 4)) : 0.f;
-  const float g0 = __ldcg(P + P_GCN0_W + src), g1 = __ldcg(P + P_GCN1_W + src);
-  const float in0 = __ldcg(P + P_MHA_IN_W + t), in1 = t < 256 ? __ldcg(P + P_MHA_IN_W + 512 + t) : 0.f;
+  const float wet = (t < 384 && (t >> 4) < F) ? __ldg(P + P_ENC_W + c * F + (t >> 4)) : 0.f;
+  const float g0 = __ldg(P + P_GCN0_W + src), g1 = __ldg(P + P_GCN1_W + src);
+  const float in0 = __ldg(P + P_MHA_IN_W + t), in1 = t < 256 ? __ldg(P + P_MHA_IN_W + 512 + t) : 0.f;
   float wq = 0.f, wk = 0.f, wv = 0.f, wo = 0.f;
   if (t < 256) {
-    wq = __ldcg(P + P_ATT_Q_W + t); wk = __ldcg(P + P_ATT_K_W + t); wv = __ldcg(P + P_ATT_V_W + t);
-    wo = __ldcg(P + P_MHA_OUT_W + t);
+    wq = __ldg(P + P_ATT_Q_W + t); wk = __ldg(P + P_ATT_K_W + t); wv = __ldg(P + P_ATT_V_W + t);
+    wo = __ldg(P + P_MHA_OUT_W + t);
   }
   float lu[4];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) lu[j] = __ldcg(P + P_LU_W0 + t + NT * j);
-  const float rd = __ldcg(P + P_RD_W0 + t);
+  for (int j = 0; j < 4; ++j) lu[j] = __ldg(P + P_LU_W0 + t + NT * j);
+  const float rd = __ldg(P + P_RD_W0 + t);
   float sm0 = 0.f, sm1 = 0.f, sm2 = 0.f;     // small vectors, one element per thread group
-  if (t < 16) { sm0 = __ldcg(P + P_ENC_B + t); sm1 = __ldcg(P + P_GCN0_B + t); sm2 = __ldcg(P + P_GCN1_B + t); }
-  else if (t < 32) { sm0 = __ldcg(P + P_MHA_OUT_B + t - 16); sm1 = __ldcg(P + P_ATT_Q_B + t - 16); sm2 = __ldcg(P + P_ATT_V_B + t - 16); }
-  else if (t < 64) { sm0 = __ldcg(P + P_LU_B0 + t - 32); sm1 = __ldcg(P + P_LU_W1 + t - 32); }
-  else if (t < 96) { sm0 = __ldcg(P + P_RD_B0 + t - 64); sm1 = __ldcg(P + P_RD_W1 + t - 64); }
-  else if (t < 112) { sm0 = __ldcg(P + P_MHA_IN_B + t - 96); sm1 = __ldcg(P + P_MHA_IN_B + 32 + t - 96); }
+  if (t < 16) { sm0 = __ldg(P + P_ENC_B + t); sm1 = __ldg(P + P_GCN0_B + t); sm2 = __ldg(P + P_GCN1_B + t); }
+  else if (t < 32) { sm0 = __ldg(P + P_MHA_OUT_B + t - 16); sm1 = __ldg(P + P_ATT_Q_B + t - 16); sm2 = __ldg(P + P_ATT_V_B + t - 16); }
+  else if (t < 64) { sm0 = __ldg(P + P_LU_B0 + t - 32); sm1 = __ldg(P + P_LU_W1 + t - 32); }
+  else if (t < 96) { sm0 = __ldg(P + P_RD_B0 + t - 64); sm1 = __ldg(P + P_RD_W1 + t - 64); }
+  else if (t < 112) { sm0 = __ldg(P + P_MHA_IN_B + t - 96); sm1 = __ldg(P + P_MHA_IN_B + 32 + t - 96); }
 
   float* tmp = sW + S_EPQ;                   // staging (the EPQ region is idle at launch time):
                                              // in_proj_weight [48][16] | Wq | Wk | Wv | bq | bv | bin_q | bin_v
@@ -793,23 +785,23 @@ __device__ __forceinline__ void stage_vn_weights(const float* __restrict__ P, fl
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   float a[5], b[2], c[8], d[2], e = 0.f;
 #pragma unroll
-  for (int j = 0; j < 5; ++j) a[j] = (t + NT * j < HID * SVD) ? __ldcg(P + P_VAL_W0 + t + NT * j) : 0.f;
+  for (int j = 0; j < 5; ++j) a[j] = (t + NT * j < HID * SVD) ? __ldg(P + P_VAL_W0 + t + NT * j) : 0.f;
 #pragma unroll
-  for (int j = 0; j < 2; ++j) b[j] = __ldcg(P + P_VAL_W1 + t + NT * j);
+  for (int j = 0; j < 2; ++j) b[j] = __ldg(P + P_VAL_W1 + t + NT * j);
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const int u = warp + NW * j;
-    c[2 * j] = __ldcg(P + P_NUM_W0 + u * NUMD + lane);
-    c[2 * j + 1] = lane < NUMD - 32 ? __ldcg(P + P_NUM_W0 + u * NUMD + 32 + lane) : 0.f;
+    c[2 * j] = __ldg(P + P_NUM_W0 + u * NUMD + lane);
+    c[2 * j + 1] = lane < NUMD - 32 ? __ldg(P + P_NUM_W0 + u * NUMD + 32 + lane) : 0.f;
   }
 #pragma unroll
-  for (int j = 0; j < 2; ++j) d[j] = __ldcg(P + P_NUM_W1 + t + NT * j);
-  if (t < 32) e = __ldcg(P + P_VAL_B0 + t);
-  else if (t < 64) e = __ldcg(P + P_VAL_B1 + t - 32);
-  else if (t < 96) e = __ldcg(P + P_VAL_W2 + t - 64);
-  else if (t < 160) e = __ldcg(P + P_NUM_B0 + t - 96);
-  else if (t < 176) e = __ldcg(P + P_NUM_B1 + t - 160);
-  else if (t == 176) e = __ldcg(P + P_VAL_B2);
+  for (int j = 0; j < 2; ++j) d[j] = __ldg(P + P_NUM_W1 + t + NT * j);
+  if (t < 32) e = __ldg(P + P_VAL_B0 + t);
+  else if (t < 64) e = __ldg(P + P_VAL_B1 + t - 32);
+  else if (t < 96) e = __ldg(P + P_VAL_W2 + t - 64);
+  else if (t < 160) e = __ldg(P + P_NUM_B0 + t - 96);
+  else if (t < 176) e = __ldg(P + P_NUM_B1 + t - 160);
+  else if (t == 176) e = __ldg(P + P_VAL_B2);
 #pragma unroll
   for (int j = 0; j < 5; ++j) if (t + NT * j < HID * SVD) vn[VN_VW0 + t + NT * j] = a[j];       // same [32][67] layout
 #pragma unroll
@@ -1132,12 +1124,12 @@ __device__ __forceinline__ void softmax_seeds(const StepArgs& a, const BlobHeade
       const float lo = 1.f - a.clip_eps, hi = 1.f + a.clip_eps;
       const float s1 = r * A, s2 = fminf(fmaxf(r, lo), hi) * A;
       surr = -fminf(s1, s2);
-      if ((r >= lo && r <= hi) || s1 < s2) glp = -A * r * sc[SC_INVI];
-      gH = -a.c_entropy * sc[SC_INVI];
+      if ((r >= lo && r <= hi) || s1 < s2) glp = -A * r * a.inv_ind;
+      gH = -a.c_entropy * a.inv_ind;
       negent = -H;
     }
     if (lane == 0) {
-      sc[SC_GV] = 2.f * a.c_value * dv * sc[SC_INVB];
+      sc[SC_GV] = 2.f * a.c_value * dv * a.inv_batch;
       float* st = gp + G_STATS;
       st[0] += dv * dv; st[1] += surr; st[2] += negent; st[3] += 1.f; st[4] += in_ind;
       st[5] += g.stage == 0 ? 1.f : 0.f; st[6] += g.stage == 1 ? 1.f : 0.f;
@@ -1438,7 +1430,7 @@ __device__ void graph_body(const StepArgs& a, const BlobHeader& hd, const GraphD
   // last, so only idle warps branch over them)
   if constexpr (TRAIN) {
     if (warp < 8) {
-      const float gV = 2.f * a.c_value * (sc[SC_VALUE] - sc[SC_RET]) * sc[SC_INVB];
+      const float gV = 2.f * a.c_value * (sc[SC_VALUE] - sc[SC_RET]) * a.inv_batch;
       value_numeric_bwd_group(sV, vn, gV, gp, tid);
     }
     if (tid >= 256 && tid < 272) sV[V_GHC + tid - 256] = 0.f;
@@ -1809,8 +1801,7 @@ __device__ __forceinline__ void adam_elem(const StepArgs& a, int i, float g, flo
 
 // Everything that does not depend on other CTAs' results is fetched or computed BEFORE the barrier it would otherwise
 // follow, so the serial part after each barrier is short.
-__device__ __noinline__ void fused_tail(const StepArgs& a, float* smem, unsigned stage_bits, float* grad_out, const long long* steps_in,
-                           long long* steps_out, unsigned seq) {
+__device__ void fused_tail(const StepArgs& a, float* smem, unsigned stage_bits) {
   constexpr int COLS = 128;                         // columns per CTA and pass, 4 threads per column
   const int tid = threadIdx.x;
   const int nparts = gridDim.x;
@@ -1821,7 +1812,7 @@ __device__ __noinline__ void fused_tail(const StepArgs& a, float* smem, unsigned
   if (tid == 0 && stage_bits) atomicOr(a.gridbar + 2, stage_bits);     // which policy heads this CTA's graphs used
   if (tid < 6) {      // Adam bias corrections of the three segments, for "head live" and "head skipped"
     const int seg = tid >> 1, live = tid & 1;
-    const long long stp = steps_in[1 + seg] + live;
+    const long long stp = a.steps_in[1 + seg] + live;
     const double bc1 = 1.0 - ipow((double)a.beta1, stp > 0 ? stp : 1);
     const double bc2 = 1.0 - ipow((double)a.beta2, stp > 0 ? stp : 1);
     sh_adam[tid * 2 + 0] = (float)((double)a.lr / bc1);
@@ -1869,7 +1860,7 @@ __device__ __noinline__ void fused_tail(const StepArgs& a, float* smem, unsigned
   const bool live_lu = bits & 1u, live_rd = bits & 2u;
   if (blockIdx.x == 0 && tid < 4) {
     // step counters: [0] global, [1] encoder+value, [2] land-use head, [3] road head
-    steps_out[tid] = tid == 0 ? steps_in[0] + 1
+    a.steps_out[tid] = tid == 0 ? a.steps_in[0] + 1
                                 : sh_steps[(tid - 1) * 2 + (tid == 1 ? 1 : (tid == 2 ? (live_lu ? 1 : 0) : (live_rd ? 1 : 0)))];
   }
   for (int c0 = blockIdx.x * COLS; c0 < G_ROW; c0 += gridDim.x * COLS) {
@@ -1894,7 +1885,7 @@ __device__ __noinline__ void fused_tail(const StepArgs& a, float* smem, unsigned
       a.gsum[col] = s;
       const bool attn = (col >= P_MHA_IN_W && col < P_MHA_OUT_W) || (col >= P_ATT_Q_W && col < P_LU_W0);
       if (col < NUM_PARAMS && !attn) {
-        grad_out[col] = s;
+        a.grad_out[col] = s;
         int seg = 0;
         bool live = true;
         if (col >= P_LU_W0 && col < P_RD_W0) { seg = 1; live = live_lu; }
@@ -1904,10 +1895,10 @@ __device__ __noinline__ void fused_tail(const StepArgs& a, float* smem, unsigned
           adam_elem(a, col, s, pm, pv, pp, sh_adam[(seg * 2 + 1) * 2], sh_adam[(seg * 2 + 1) * 2 + 1]);
         }
       } else if (col >= NUM_PARAMS && col < UPB_STAT_OFFSET) {
-        grad_out[col] = 0.f;
+        a.grad_out[col] = 0.f;
       }
-      if (col >= G_STATS && col < G_STATS + 8) grad_out[UPB_STAT_OFFSET + (col - G_STATS)] = s;
-      if (col >= G_STATS + 8 && col < G_STATS + UPB_STAT_COUNT) grad_out[UPB_STAT_OFFSET + (col - G_STATS)] = 0.f;
+      if (col >= G_STATS && col < G_STATS + 8) a.grad_out[UPB_STAT_OFFSET + (col - G_STATS)] = s;
+      if (col >= G_STATS + 8 && col < G_STATS + UPB_STAT_COUNT) a.grad_out[UPB_STAT_OFFSET + (col - G_STATS)] = 0.f;
     }
   }
   UPB_TSTAMP(42);
@@ -1953,7 +1944,7 @@ __device__ __noinline__ void fused_tail(const StepArgs& a, float* smem, unsigned
     const int i = tid + j * NT;
     if (i < 1632) {
       const float g = sOut[i];
-      grad_out[cdst[j]] = g;
+      a.grad_out[cdst[j]] = g;
       adam_elem(a, cdst[j], g, cm[j], cv[j], cp[j], sh_adam[2], sh_adam[3]);     // segment 0 (encoder), live
     }
   }
@@ -1971,8 +1962,7 @@ __device__ __noinline__ void fused_tail(const StepArgs& a, float* smem, unsigned
 //   chains them.  Same summation order on every rank -> bit-identical parameters everywhere, no NCCL call, one launch
 //   per optimiser step.  The exchange buffer is double-buffered by step parity: a rank can only be one step ahead of
 //   the slowest one (it needs that rank's flag of the current step), so parity p is never rewritten while it is read.
-__device__ __noinline__ void fused_tail_peers(const StepArgs& a, float* smem, unsigned stage_bits, float* grad_out, const long long* steps_in,
-                           long long* steps_out, unsigned seq) {
+__device__ void fused_tail_peers(const StepArgs& a, float* smem, unsigned stage_bits) {
   constexpr int COLS = 128;
   const int tid = threadIdx.x;
   const int nparts = gridDim.x;
@@ -1982,12 +1972,12 @@ __device__ __noinline__ void fused_tail_peers(const StepArgs& a, float* smem, un
   __shared__ int sh_live[2];
   __shared__ int sh_timeout;
   __shared__ const float* sh_peer[MAX_PEERS];
-  const unsigned par = seq & 1u;
+  const unsigned par = a.seq & 1u;
   if (tid < world) sh_peer[tid] = a.peers[tid] + (size_t)par * G_ROW;
   if (tid == 32) { sh_timeout = 0; sh_live[0] = 0; sh_live[1] = 0; }
   if (tid < 6) {
     const int seg = tid >> 1, live = tid & 1;
-    const long long stp = steps_in[1 + seg] + live;
+    const long long stp = a.steps_in[1 + seg] + live;
     const double bc1 = 1.0 - ipow((double)a.beta1, stp > 0 ? stp : 1);
     const double bc2 = 1.0 - ipow((double)a.beta2, stp > 0 ? stp : 1);
     sh_adam[tid * 2 + 0] = (float)((double)a.lr / bc1);
@@ -2059,13 +2049,13 @@ __device__ __noinline__ void fused_tail_peers(const StepArgs& a, float* smem, un
       unsigned* row = reinterpret_cast<unsigned*>(a.peers[tid] + XCHG_FLAGS) + par * 2 * MAX_PEERS;
       __threadfence_system();
       asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(row + MAX_PEERS + a.rank), "r"(bits) : "memory");
-      st_release_sys(row + a.rank, seq);
+      st_release_sys(row + a.rank, a.seq);
     }
   }
   if (tid < world) {                                // all ranks (this one included) have published this step
     const unsigned* row = reinterpret_cast<const unsigned*>(a.peers[a.rank] + XCHG_FLAGS) + par * 2 * MAX_PEERS;
     unsigned polls = 0;
-    while ((int)(ld_acquire_sys(row + tid) - seq) < 0) {
+    while ((int)(ld_acquire_sys(row + tid) - a.seq) < 0) {
       if (++polls >= PEER_SPIN_LIMIT) { sh_timeout = 1; break; }
     }
     unsigned bits;
@@ -2077,7 +2067,7 @@ __device__ __noinline__ void fused_tail_peers(const StepArgs& a, float* smem, un
   __syncthreads();
   const bool live_lu = sh_live[0], live_rd = sh_live[1];
   if (blockIdx.x == 0 && tid < 4) {
-    steps_out[tid] = tid == 0 ? steps_in[0] + 1
+    a.steps_out[tid] = tid == 0 ? a.steps_in[0] + 1
                                 : sh_steps[(tid - 1) * 2 + (tid == 1 ? 1 : (tid == 2 ? (live_lu ? 1 : 0) : (live_rd ? 1 : 0)))];
   }
   // All peer loads of a thread are issued before the first use: one NVLink round trip per phase, not one per rank.
@@ -2105,7 +2095,7 @@ __device__ __noinline__ void fused_tail_peers(const StepArgs& a, float* smem, un
       a.gsum[col] = s;
       const bool attn = (col >= P_MHA_IN_W && col < P_MHA_OUT_W) || (col >= P_ATT_Q_W && col < P_LU_W0);
       if (col < NUM_PARAMS && !attn) {
-        grad_out[col] = s;
+        a.grad_out[col] = s;
         int seg = 0;
         bool live = true;
         if (col >= P_LU_W0 && col < P_RD_W0) { seg = 1; live = live_lu; }
@@ -2115,10 +2105,10 @@ __device__ __noinline__ void fused_tail_peers(const StepArgs& a, float* smem, un
           adam_elem(a, col, s, pm, pv, pp, sh_adam[(seg * 2 + 1) * 2], sh_adam[(seg * 2 + 1) * 2 + 1]);
         }
       } else if (col >= NUM_PARAMS && col < UPB_STAT_OFFSET) {
-        grad_out[col] = 0.f;
+        a.grad_out[col] = 0.f;
       }
-      if (col >= G_STATS && col < G_STATS + 8) grad_out[UPB_STAT_OFFSET + (col - G_STATS)] = s;
-      if (col >= G_STATS + 8 && col < G_STATS + UPB_STAT_COUNT) grad_out[UPB_STAT_OFFSET + (col - G_STATS)] = 0.f;
+      if (col >= G_STATS && col < G_STATS + 8) a.grad_out[UPB_STAT_OFFSET + (col - G_STATS)] = s;
+      if (col >= G_STATS + 8 && col < G_STATS + UPB_STAT_COUNT) a.grad_out[UPB_STAT_OFFSET + (col - G_STATS)] = 0.f;
     }
   }
   if (blockIdx.x != 0) return;
@@ -2166,7 +2156,7 @@ __device__ __noinline__ void fused_tail_peers(const StepArgs& a, float* smem, un
     const int i = tid + j * NT;
     if (i < 1632) {
       const float g = sOut[i];
-      grad_out[cdst[j]] = g;
+      a.grad_out[cdst[j]] = g;
       adam_elem(a, cdst[j], g, cm[j], cv[j], cp[j], sh_adam[2], sh_adam[3]);
     }
   }
@@ -2178,75 +2168,56 @@ template <bool TRAIN>
 __global__ void __launch_bounds__(NT, 1) k_sgnn(const __grid_constant__ StepArgs a) {
   extern __shared__ __align__(16) float smem[];
   const long long t_cta0 = a.stamps ? clock64() : 0;
+  load_weights(a.params, smem);
   float* gp = nullptr;
-  if constexpr (TRAIN) gp = a.gpart + (size_t)blockIdx.x * G_ROW;
+  if constexpr (TRAIN) {
+    gp = a.gpart + (size_t)blockIdx.x * G_ROW;
+    for (int i = threadIdx.x; i < G_ROW / 4; i += NT) reinterpret_cast<float4*>(gp)[i] = f4(0.f);
+  }
+  __syncthreads();
+  if (a.stamps && threadIdx.x == 0 && blockIdx.x < 160) a.stamps[64 + 160 + blockIdx.x] = clock64() - t_cta0;   // launch prologue
   const BlobHeader& hd = *reinterpret_cast<const BlobHeader*>(a.blob);
   const GraphDesc* descs = reinterpret_cast<const GraphDesc*>(a.blob + hd.off_desc);
   float* scr = a.scratch + (size_t)blockIdx.x * a.scratch_stride;
-  const int nsteps = (TRAIN && a.num_steps > 1) ? a.num_steps : 1;
-  for (int step = 0; step < nsteps; ++step) {
-    // (parameters are re-read every step with L2-coherent loads: the previous step's Adam ran on other SMs)
-    load_weights(a.params, smem);
-    if constexpr (TRAIN) {
-      for (int i = threadIdx.x; i < G_ROW / 4; i += NT) reinterpret_cast<float4*>(gp)[i] = f4(0.f);
+  unsigned stage_bits = 0;     // bit 0: a land-use graph, bit 1: a road graph was walked by this CTA
+  for (int item = blockIdx.x; item < a.count; item += gridDim.x) {
+    const int gid = a.ids ? a.ids[item] : item;
+    const GraphDesc d = descs[gid];
+    stage_bits |= 1u << (d.stage & 1);
+    if (d.n > a.n_cap || d.e > a.e_cap || d.n < 1) {   // larger than the context was sized for: skip, flag
+      if (threadIdx.x == 0) {
+        if constexpr (TRAIN) gp[G_STATS + 7] += 1.f;
+        if (a.out_value) a.out_value[gid] = CUDART_NAN_F;
+        if (a.out_logp) a.out_logp[gid] = CUDART_NAN_F;
+        if (a.out_entropy) a.out_entropy[gid] = CUDART_NAN_F;
+      }
+      continue;
     }
-    const int* ids = a.ids ? a.ids + (size_t)step * a.ids_stride : nullptr;
-    const int count = a.step_counts ? a.step_counts[step] : a.count;
-    if (threadIdx.x < 2)
-      smem[S_VEC + V_STEP + threadIdx.x] = a.step_scales ? a.step_scales[2 * step + threadIdx.x]
-                                                         : (threadIdx.x == 0 ? a.inv_batch : a.inv_ind);
+    {   // pull the NEXT graph of this CTA into L2 while this one is processed (its first touches are then L2 hits)
+      const int nitem = item + gridDim.x;
+      if (nitem < a.count) {
+        const GraphDesc& nd = descs[a.ids ? a.ids[nitem] : nitem];
+        const char* px = reinterpret_cast<const char*>(a.blob + hd.off_x) + (size_t)nd.x_row * FS * 4;
+        const char* pa = reinterpret_cast<const char*>(a.blob + hd.off_adj) + (size_t)nd.adj_off * 4;
+        const char* pr = reinterpret_cast<const char*>(a.blob + hd.off_rowptr) + (size_t)nd.rp_off * 2;
+        const char* po = reinterpret_cast<const char*>(a.blob + hd.off_order) + (size_t)nd.ord_off * 2;
+        const int bx = nd.n * FS * 4, ba = nd.e * 8, br = (nd.n + 1) * 2, bo = nd.ord_rounds * NW * 16;
+        for (int o = threadIdx.x * 128; o < bx; o += NT * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(px + o));
+        for (int o = threadIdx.x * 128; o < ba; o += NT * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pa + o));
+        for (int o = threadIdx.x * 128; o < br; o += NT * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pr + o));
+        for (int o = threadIdx.x * 128; o < bo; o += NT * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(po + o));
+      }
+    }
+    const bool big = d.n > NS || 2 * d.e > AS || d.k > KS || d.ord_rounds > ORD_ROUNDS;
+    if (big) graph_body<TRAIN, true>(a, hd, d, gid, smem, gp, scr, item == (int)(blockIdx.x + gridDim.x));   // stamps: the SECOND graph of CTA 0 (steady state)
+    else graph_body<TRAIN, false>(a, hd, d, gid, smem, gp, scr, item == (int)(blockIdx.x + gridDim.x));   // stamps: the SECOND graph of CTA 0 (steady state)
     __syncthreads();
-    if (step == 0 && a.stamps && threadIdx.x == 0 && blockIdx.x < 160) a.stamps[64 + 160 + blockIdx.x] = clock64() - t_cta0;   // launch prologue
-    unsigned stage_bits = 0;     // bit 0: a land-use graph, bit 1: a road graph was walked by this CTA
-    for (int item = blockIdx.x; item < count; item += gridDim.x) {
-      const int gid = ids ? ids[item] : item;
-      const GraphDesc d = descs[gid];
-      stage_bits |= 1u << (d.stage & 1);
-      if (d.n > a.n_cap || d.e > a.e_cap || d.n < 1) {   // larger than the context was sized for: skip, flag
-        if (threadIdx.x == 0) {
-          if constexpr (TRAIN) gp[G_STATS + 7] += 1.f;
-          if (a.out_value) a.out_value[gid] = CUDART_NAN_F;
-          if (a.out_logp) a.out_logp[gid] = CUDART_NAN_F;
-          if (a.out_entropy) a.out_entropy[gid] = CUDART_NAN_F;
-        }
-        continue;
-      }
-      {   // pull the NEXT graph of this CTA into L2 while this one is processed (its first touches are then L2 hits)
-        const int nitem = item + gridDim.x;
-        if (nitem < count) {
-          const GraphDesc& nd = descs[ids ? ids[nitem] : nitem];
-          const char* px = reinterpret_cast<const char*>(a.blob + hd.off_x) + (size_t)nd.x_row * FS * 4;
-          const char* pa = reinterpret_cast<const char*>(a.blob + hd.off_adj) + (size_t)nd.adj_off * 4;
-          const char* pr = reinterpret_cast<const char*>(a.blob + hd.off_rowptr) + (size_t)nd.rp_off * 2;
-          const char* po = reinterpret_cast<const char*>(a.blob + hd.off_order) + (size_t)nd.ord_off * 2;
-          const int bx = nd.n * FS * 4, ba = nd.e * 8, br = (nd.n + 1) * 2, bo = nd.ord_rounds * NW * 16;
-          for (int o = threadIdx.x * 128; o < bx; o += NT * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(px + o));
-          for (int o = threadIdx.x * 128; o < ba; o += NT * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pa + o));
-          for (int o = threadIdx.x * 128; o < br; o += NT * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pr + o));
-          for (int o = threadIdx.x * 128; o < bo; o += NT * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(po + o));
-        }
-      }
-      const bool big = d.n > NS || 2 * d.e > AS || d.k > KS || d.ord_rounds > ORD_ROUNDS;
-      const bool stamped = step == 0 && item == (int)(blockIdx.x + gridDim.x);   // stamps: the SECOND graph of CTA 0 (steady state)
-      if (big) graph_body<TRAIN, true>(a, hd, d, gid, smem, gp, scr, stamped);
-      else graph_body<TRAIN, false>(a, hd, d, gid, smem, gp, scr, stamped);
-      __syncthreads();
-    }
-    if (step == 0 && a.stamps && threadIdx.x == 0 && blockIdx.x < 160) a.stamps[64 + blockIdx.x] = clock64() - t_cta0;   // CTA busy time
-    if constexpr (TRAIN) {
-      if (a.fuse_tail) {
-        const long long* steps_in = a.steps_base + 4 * ((a.steps_cur + step) & 1);
-        long long* steps_out = const_cast<long long*>(a.steps_base) + 4 * ((a.steps_cur + step + 1) & 1);
-        float* grad_out = a.grad_out + (size_t)step * UPB_GRAD_STRIDE;
-        if (a.world > 1) fused_tail_peers(a, smem, stage_bits, grad_out, steps_in, steps_out, a.seq + (unsigned)step);
-        else fused_tail(a, smem, stage_bits, grad_out, steps_in, steps_out, a.seq + (unsigned)step);
-        if (step + 1 < nsteps) {          // everybody's Adam has landed before anybody reloads the parameters
-          grid_arrive(a.gridbar + 3);
-          grid_wait(a.gridbar + 3, (unsigned)(step + 1) * gridDim.x);
-        } else if (nsteps > 1 && blockIdx.x == 0 && threadIdx.x == 0) {
-          a.gridbar[3] = 0u;              // every CTA passed the last step barrier before it reached this step's first one
-        }
-      }
+  }
+  if (a.stamps && threadIdx.x == 0 && blockIdx.x < 160) a.stamps[64 + blockIdx.x] = clock64() - t_cta0;           // CTA busy time
+  if constexpr (TRAIN) {
+    if (a.fuse_tail) {
+      if (a.world > 1) fused_tail_peers(a, smem, stage_bits);
+      else fused_tail(a, smem, stage_bits);
     }
   }
 }

@@ -292,72 +292,13 @@ extern "C" int upb_apply(upb_ctx* ctx, float* params, const float* grad, void* s
   return UPB_OK;
 }
 
-namespace {
-
-// One cooperative launch that runs `num_steps` optimiser steps (gradient, reduction over CTAs and ranks, Adam each).
-int launch_fused_steps(upb_ctx* ctx, const char* who, const void* blob_dev, const int32_t* ids, int ids_stride,
-                       const int32_t* step_counts, const float* step_scales, int num_steps, int count, float inv_batch,
-                       float inv_ind, float* params, const float* actions, const float* advantages,
-                       const float* returns, const float* fixed_log_probs, const float* exps, float* grad_out,
-                       void* stream) {
-  if (!blob_dev || !params || !actions || !advantages || !returns || !fixed_log_probs || !exps || !grad_out) {
-    char buf[96];
-    snprintf(buf, sizeof(buf), "%s: bad argument", who);
-    return set_error(UPB_ERR_ARG, buf);
-  }
-  cudaStream_t s = (cudaStream_t)stream;
-  StepArgs a = base_args(ctx, blob_dev, ids, count, params, actions);
-  a.adv = advantages;
-  a.ret = returns;
-  a.fixed_lp = fixed_log_probs;
-  a.exps = exps;
-  a.inv_batch = inv_batch;
-  a.inv_ind = inv_ind;
-  a.fuse_tail = 1;
-  a.num_steps = num_steps;
-  a.ids_stride = ids_stride;
-  a.step_counts = step_counts;
-  a.step_scales = step_scales;
-  a.params_rw = params;
-  a.gsum = ctx->gsum;
-  a.grad_out = grad_out;
-  a.adam_m = ctx->adam_m;
-  a.adam_v = ctx->adam_v;
-  a.steps_base = ctx->steps;
-  a.steps_cur = ctx->steps_cur;
-  a.gridbar = ctx->gridbar;
-  a.lr = ctx->cfg.lr;
-  a.beta1 = ctx->cfg.beta1;
-  a.beta2 = ctx->cfg.beta2;
-  a.adam_eps = ctx->cfg.adam_eps;
-  a.world = ctx->world;
-  a.rank = ctx->rank;
-  a.seq = ctx->world > 1 ? ctx->peer_seq + 1 : 0u;
-  a.peers = ctx->peers_dev;
-  const int grid = count < 1 ? 1 : (count < ctx->grid ? count : ctx->grid);     // an empty shard still takes part in the exchange
-  void* kargs[] = {&a};
-  const bool prof = prof_begin(ctx, s);
-  UPB_CUDA(cudaLaunchCooperativeKernel((void*)k_sgnn<true>, dim3(grid), dim3(NT), kargs, SMEM_BYTES, s));
-  prof_end(ctx, s, prof);
-  ctx->launches += 1;
-  if (ctx->world > 1) ctx->peer_seq += (unsigned)num_steps;
-  ctx->steps_cur = (ctx->steps_cur + num_steps) & 1;
-  ctx->host_steps += num_steps;
-  return UPB_OK;
-}
-
-bool clips_next(const upb_ctx* ctx) {
-  return ctx->cfg.clip_mode == UPB_CLIP_ALWAYS || (ctx->cfg.clip_mode == UPB_CLIP_REFERENCE && ctx->host_steps == 0);
-}
-
-}  // namespace
-
 extern "C" int upb_ppo_step(upb_ctx* ctx, const void* blob_dev, const int32_t* ids, int count, float* params,
                             const float* actions, const float* advantages, const float* returns,
                             const float* fixed_log_probs, const float* exps, float inv_batch, float inv_ind,
                             float* grad_out, void* stream) {
   if (int rc = check_ctx(ctx, "ppo_step")) return rc;
-  const bool clip_now = clips_next(ctx);
+  const bool clip_now = ctx->cfg.clip_mode == UPB_CLIP_ALWAYS ||
+                        (ctx->cfg.clip_mode == UPB_CLIP_REFERENCE && ctx->host_steps == 0);
   if (ctx->world > 1) {
     if (clip_now || !ctx->coop)
       return set_error(UPB_ERR_ARG, "ppo_step: peers are connected and this step clips gradients; use upb_ppo_grad + "
@@ -368,24 +309,42 @@ extern "C" int upb_ppo_step(upb_ctx* ctx, const void* blob_dev, const int32_t* i
     if (rc != UPB_OK) return rc;
     return upb_apply(ctx, params, grad_out, stream);
   }
-  return launch_fused_steps(ctx, "ppo_step", blob_dev, ids, 0, nullptr, nullptr, 1, count, inv_batch, inv_ind, params,
-                            actions, advantages, returns, fixed_log_probs, exps, grad_out, stream);
-}
-
-extern "C" int upb_ppo_steps(upb_ctx* ctx, const void* blob_dev, const int32_t* ids, int ids_stride,
-                             const int32_t* step_counts, const float* step_scales, int num_steps, int max_count,
-                             float* params, const float* actions, const float* advantages, const float* returns,
-                             const float* fixed_log_probs, const float* exps, float* grad_out, void* stream) {
-  if (int rc = check_ctx(ctx, "ppo_steps")) return rc;
-  if (num_steps < 1 || num_steps > 4096 || !ids || !step_counts || !step_scales || ids_stride < 1 || max_count < 0 ||
-      max_count > ids_stride)
-    return set_error(UPB_ERR_ARG, "ppo_steps: need 1 <= num_steps <= 4096, ids / step_counts / step_scales and "
-                                  "0 <= max_count <= ids_stride");
-  if (clips_next(ctx) || !ctx->coop)
-    return set_error(UPB_ERR_ARG, "ppo_steps: the next step clips gradients (or cooperative launch is unavailable); "
-                                  "run it with upb_ppo_step / the three-call path first (upb_next_step_fused() == 0)");
-  return launch_fused_steps(ctx, "ppo_steps", blob_dev, ids, ids_stride, step_counts, step_scales, num_steps, max_count,
-                            0.f, 0.f, params, actions, advantages, returns, fixed_log_probs, exps, grad_out, stream);
+  if (!blob_dev || !params || !actions || !advantages || !returns || !fixed_log_probs || !exps || !grad_out)
+    return set_error(UPB_ERR_ARG, "ppo_step: bad argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  StepArgs a = base_args(ctx, blob_dev, ids, count, params, actions);
+  a.adv = advantages;
+  a.ret = returns;
+  a.fixed_lp = fixed_log_probs;
+  a.exps = exps;
+  a.inv_batch = inv_batch;
+  a.inv_ind = inv_ind;
+  a.fuse_tail = 1;
+  a.params_rw = params;
+  a.gsum = ctx->gsum;
+  a.grad_out = grad_out;
+  a.adam_m = ctx->adam_m;
+  a.adam_v = ctx->adam_v;
+  a.steps_in = ctx->steps + 4 * ctx->steps_cur;
+  a.steps_out = ctx->steps + 4 * (1 - ctx->steps_cur);
+  a.gridbar = ctx->gridbar;
+  a.lr = ctx->cfg.lr;
+  a.beta1 = ctx->cfg.beta1;
+  a.beta2 = ctx->cfg.beta2;
+  a.adam_eps = ctx->cfg.adam_eps;
+  a.world = ctx->world;
+  a.rank = ctx->rank;
+  a.seq = ctx->world > 1 ? ++ctx->peer_seq : 0u;
+  a.peers = ctx->peers_dev;
+  const int grid = count < 1 ? 1 : (count < ctx->grid ? count : ctx->grid);     // an empty shard still takes part in the exchange
+  void* kargs[] = {&a};
+  const bool prof = prof_begin(ctx, s);
+  UPB_CUDA(cudaLaunchCooperativeKernel((void*)k_sgnn<true>, dim3(grid), dim3(NT), kargs, SMEM_BYTES, s));
+  prof_end(ctx, s, prof);
+  ctx->launches += 1;
+  ctx->steps_cur = 1 - ctx->steps_cur;
+  ctx->host_steps += 1;
+  return UPB_OK;
 }
 
 // ---- multi-GPU fused step: exchange buffers shared between the ranks' processes with CUDA IPC ---------------------------
@@ -439,7 +398,9 @@ extern "C" int upb_peer_connect(upb_ctx* ctx, int world, int rank, const void* h
 
 extern "C" int upb_next_step_fused(upb_ctx* ctx) {
   if (!ctx) return 0;
-  return (!clips_next(ctx) && ctx->coop) ? 1 : 0;
+  const bool clip_now = ctx->cfg.clip_mode == UPB_CLIP_ALWAYS ||
+                        (ctx->cfg.clip_mode == UPB_CLIP_REFERENCE && ctx->host_steps == 0);
+  return (!clip_now && ctx->coop) ? 1 : 0;
 }
 
 extern "C" int upb_read_losses(upb_ctx* ctx, const float* grad, float* out4_host, void* stream) {

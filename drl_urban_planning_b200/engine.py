@@ -159,27 +159,6 @@ class Engine:
             "upb_ppo_step")
         return out
 
-    def ppo_steps(self, blob: PackedGraphs, params: torch.Tensor, actions: torch.Tensor, advantages: torch.Tensor,
-                  returns: torch.Tensor, fixed_log_probs: torch.Tensor, exps: torch.Tensor, ids: torch.Tensor,
-                  counts: torch.Tensor, scales: torch.Tensor, max_count: int, out: Optional[torch.Tensor] = None
-                  ) -> torch.Tensor:
-        """Several optimiser steps in one launch (upb_ppo_steps): ids int32 [S, W] (row s = the graphs of step s, the
-        first counts[s] entries valid), counts int32 [S], scales float32 [S, 2] = (1/B, 1/|ind|) per step, all on the
-        device.  Returns the [S, UPB_GRAD_STRIDE] gradient / statistics reports.  Needs next_step_fused()."""
-        self._check_blob(blob)
-        dev = self.device
-        S, W = int(ids.shape[0]), int(ids.shape[1])
-        assert ids.dtype == torch.int32 and ids.is_contiguous() and counts.dtype == torch.int32 and counts.numel() == S
-        assert scales.dtype == torch.float32 and scales.is_contiguous() and scales.numel() == 2 * S
-        if out is None or out.numel() < S * _lib.UPB_GRAD_STRIDE:
-            out = torch.zeros(S, _lib.UPB_GRAD_STRIDE, dtype=torch.float32, device=dev)
-        _lib.check(_lib.lib().upb_ppo_steps(
-            self._ctx, blob.dev_ptr(), ids.data_ptr(), W, counts.data_ptr(), scales.data_ptr(), S, int(max_count),
-            params.data_ptr(), _f32(actions, dev).data_ptr(), _f32(advantages, dev).data_ptr(),
-            _f32(returns, dev).data_ptr(), _f32(fixed_log_probs, dev).data_ptr(), _f32(exps, dev).data_ptr(),
-            out.data_ptr(), self._stream()), "upb_ppo_steps")
-        return out
-
     def select_action(self, blob: PackedGraphs, params: torch.Tensor, uniforms: Optional[torch.Tensor] = None,
                       ids: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Action index per graph of the blob (int32, indexed by blob position): greedy arg-max when `uniforms` is

@@ -9,9 +9,7 @@ scalars per minibatch -- but a different data path:
     (the reference re-tensorfies every state for each of the 2 + epochs sweeps);
   * a minibatch is an int32 index list into the resident blob, so a step moves ~1 KB H2D;
   * one encoder pass yields value, log-prob and entropy (the reference runs the encoder twice per step);
-  * loss scalars stay on the device and are read back once per epoch (the reference syncs 4x per step);
-  * the steps of an epoch run in ONE cooperative launch (`upb_ppo_steps`): their index lists and 1/B, 1/|ind| are known
-    when the epoch starts; only a step that clips gradients (the reference's first one) is issued on its own.
+  * loss scalars stay on the device and are read back once per epoch (the reference syncs 4x per step).
 
 Data parallel: every rank holds the whole buffer and takes `perm[i*B:(i+1)*B][rank::world]` of each global minibatch;
 1/B and 1/|ind| are global, so the summed shard gradients equal the single-GPU batch gradient (SURVEY.md section
@@ -75,7 +73,6 @@ class PPOUpdater:
         self.blob: Optional[PackedGraphs] = None
         self._dev_blob_buf = None
         self.loss_iter = 0
-        self._multi_grad = None
 
     # ------------------------------------------------------------------ buffer
     def load_states(self, states: Sequence, actions, exps=None):
@@ -147,32 +144,11 @@ class PPOUpdater:
             for i, x in enumerate(shards):
                 ids_host[i, :len(x)] = x
             ids_dev = torch.as_tensor(ids_host).to(self.device)
-            n_inds = [int((self.exps_host[perm[i * B:min((i + 1) * B, T)]] != 0).sum()) for i in range(nb)]
-            sizes = [min((i + 1) * B, T) - i * B for i in range(nb)]
-            first = 0
-            fused = self.world == 1 or self.fused_exchange
-            if nb > 0 and not (fused and self.engine.next_step_fused()):
-                # a step that clips gradients (the reference clips on its very first optimiser step only, A.6-2) or a
-                # group without peer access: one call sequence per step
-                last = nb if not fused else 1
-                for i in range(last):
-                    self.minibatch_step(ids_dev[i, :len(shards[i])], sizes[i], n_inds[i])
-                    stats_all[i].copy_(self.grad[_lib.UPB_STAT_OFFSET:_lib.UPB_STAT_OFFSET + 8])
-                first = last
-            if first < nb:
-                # the rest of the epoch in ONE cooperative launch: every step's index list, graph count and 1/B, 1/|ind|
-                # are known up front (reference :306-322); parameters are updated in place between the steps
-                S = nb - first
-                counts = torch.as_tensor(np.array([len(x) for x in shards[first:]], np.int32)).to(self.device)
-                scales = torch.as_tensor(np.array([[1.0 / max(sizes[i], 1), 1.0 / max(n_inds[i], 1)]
-                                                   for i in range(first, nb)], np.float32)).to(self.device)
-                if self._multi_grad is None or self._multi_grad.shape[0] < S:
-                    self._multi_grad = torch.zeros(S, _lib.UPB_GRAD_STRIDE, dtype=torch.float32, device=self.device)
-                out = self.engine.ppo_steps(self.blob, self.params, self.actions, self.advantages, self.returns,
-                                            self.fixed_log_probs, self.exps, ids_dev[first:].contiguous(), counts,
-                                            scales, max(len(x) for x in shards[first:]), out=self._multi_grad)
-                stats_all[first:nb].copy_(out[:S, _lib.UPB_STAT_OFFSET:_lib.UPB_STAT_OFFSET + 8])
-                self.grad.copy_(out[S - 1])
+            for i in range(nb):
+                sl = slice(i * B, min((i + 1) * B, T))
+                n_ind = int((self.exps_host[perm[sl]] != 0).sum())
+                self.minibatch_step(ids_dev[i, :len(shards[i])], sl.stop - sl.start, n_ind)
+                stats_all[i].copy_(self.grad[_lib.UPB_STAT_OFFSET:_lib.UPB_STAT_OFFSET + 8])
             st = stats_all[:nb].cpu().numpy().astype(np.float64)                       # one sync per epoch
             nB, nI = np.maximum(st[:, 3], 1), np.maximum(st[:, 4], 1)
             vl, sl_, el = st[:, 0] / nB, st[:, 1] / nI, st[:, 2] / nI

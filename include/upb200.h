@@ -162,18 +162,6 @@ int upb_peer_export(upb_ctx* ctx, void* handle_out);
 int upb_peer_connect(upb_ctx* ctx, int world, int rank, const void* handles);
 int upb_next_step_fused(upb_ctx* ctx);
 
-/* `num_steps` consecutive optimiser steps in ONE cooperative launch (the minibatches of a PPO epoch are known up
- * front: urban_planning_agent.py:306-322).  Step s processes the step_counts[s] graphs ids[s * ids_stride ...], with
- * step_scales[2 s] = 1/B and step_scales[2 s + 1] = 1/|ind| (device arrays), and writes its gradient / statistics
- * report to grad_out + s * UPB_GRAD_STRIDE; the parameters are updated in place after every step and re-read by the
- * next one behind a grid barrier.  Identical results to num_steps calls of upb_ppo_step; saves the launch gap and
- * keeps one launch per epoch.  max_count = max over s of step_counts[s] (sizes the grid).  None of the steps may
- * clip gradients (upb_next_step_fused() == 1 before the call; CLIP_REFERENCE clips only the very first step). */
-int upb_ppo_steps(upb_ctx* ctx, const void* blob_dev, const int32_t* ids, int ids_stride, const int32_t* step_counts,
-                  const float* step_scales, int num_steps, int max_count, float* params, const float* actions,
-                  const float* advantages, const float* returns, const float* fixed_log_probs, const float* exps,
-                  float* grad_out, void* stream);
-
 /* the 4 scalars the reference logs per minibatch (urban_planning_agent.py:338-345), from a gradient buffer:
  * out4 = {loss, value_loss, surr_loss, entropy_loss}.  Synchronises `stream`. */
 int upb_read_losses(upb_ctx* ctx, const float* grad, float* out4_host, void* stream);

@@ -371,48 +371,3 @@ def test_select_action_greedy_and_sampled(dev):
     ids = torch.as_tensor(np.array([5, 7, 11], np.int32), device=dev)
     part = eng.select_action(blob, params, uniforms=t(u, dev), ids=ids).cpu().numpy()
     assert np.array_equal(part[[5, 7, 11]], picked[[5, 7, 11]]) and part[[0, 1, 2]].tolist() == [0, 0, 0]
-
-
-def test_multi_step_launch_matches_single_steps(dev):
-    """upb_ppo_steps (several optimiser steps in one cooperative launch, parameters re-read behind a grid barrier)
-    against the same steps issued one by one with upb_ppo_step: bit-identical parameters, Adam state and per-step
-    reports; ragged index lists (different graph counts per step, one of them larger than the SM count is not needed
-    here: the grid is sized by the largest), a head that is absent in some steps, and the refusal on a clipping step."""
-    count = 96
-    states, actions = synth.make_states(61, "small", count)
-    adv, ret, exps = synth.make_ppo_targets(61, count)
-    exps[5] = 0.0
-    flat = PL.default_init(61)
-    fixed = np.full((count, 1), -3.1, np.float32)
-    blob = pack_states(states).to(dev)
-    a = (t(actions, dev), t(adv, dev), t(ret, dev), t(fixed, dev), t(exps, dev))
-    rng = np.random.default_rng(61)
-    stage = blob.info[:, 3]
-    lists = [rng.permutation(count)[:m] for m in (40, 17, 64, 1, 33)]
-    lists.append(np.flatnonzero(stage == 0)[:20])                     # a step without road graphs: that head is skipped
-    S, W = len(lists), max(len(x) for x in lists)
-    ids = np.zeros((S, W), np.int32)
-    for s, x in enumerate(lists):
-        ids[s, :len(x)] = x
-    counts = np.array([len(x) for x in lists], np.int32)
-    scales = np.array([[1.0 / len(x), 1.0 / max(int((exps[x] != 0).sum()), 1)] for x in lists], np.float32)
-    e1, e2 = make_engine(dev, blob.n_cap, blob.e_cap), make_engine(dev, blob.n_cap, blob.e_cap)
-    p1, p2 = t(flat, dev).clone(), t(flat, dev).clone()
-    with pytest.raises(_lib.UpbError, match="clips"):                  # the very first step clips (reference quirk)
-        e2.ppo_steps(blob, p2, *a, t(ids, dev), t(counts, dev), t(scales, dev), W)
-    for e, p in ((e1, p1), (e2, p2)):
-        e.ppo_step(blob, p, *a, 1.0 / count, 1.0 / (count - 1))
-    reports = []
-    for s, x in enumerate(lists):
-        g = e1.ppo_step(blob, p1, *a, float(scales[s, 0]), float(scales[s, 1]), ids=t(ids[s, :len(x)].copy(), dev))
-        reports.append(g.clone())
-    out = e2.ppo_steps(blob, p2, *a, t(ids, dev), t(counts, dev), t(scales, dev), W)
-    torch.cuda.synchronize()
-    assert torch.equal(p1, p2)
-    for s in range(S):
-        assert torch.equal(out[s], reports[s]), s
-    m1, v1, s1 = e1.get_opt_state(); m2, v2, s2 = e2.get_opt_state()
-    assert np.array_equal(m1, m2) and np.array_equal(v1, v2) and s1.tolist() == s2.tolist()
-    # and the engines keep working step by step afterwards
-    e1.ppo_step(blob, p1, *a, 1.0 / count, 1.0 / (count - 1)); e2.ppo_step(blob, p2, *a, 1.0 / count, 1.0 / (count - 1))
-    assert torch.equal(p1, p2)
