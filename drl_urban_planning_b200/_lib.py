@@ -54,6 +54,7 @@ _PROTOS = {
     "upb_gae": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int, C.c_float, C.c_float, _VP, _VP, _VP]),
     "upb_get_opt_state": (C.c_int, [_VP, _VP, _VP, _VP]),
     "upb_set_opt_state": (C.c_int, [_VP, _VP, _VP, _VP]),
+    "upb_rearm_clip": (C.c_int, [_VP]),
     "upb_profile_enable": (C.c_int, [_VP, C.c_int]),
     "upb_profile_read": (C.c_int, [_VP, C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "upb_grid_size": (C.c_int, [_VP]),
@@ -63,6 +64,7 @@ _PROTOS = {
     "upb_peer_export": (C.c_int, [_VP, _VP]),
     "upb_peer_connect": (C.c_int, [_VP, C.c_int, C.c_int, _VP]),
     "upb_next_step_fused": (C.c_int, [_VP]),
+    "upb_peer_timeouts": (C.c_int, [_VP, C.POINTER(C.c_int64)]),
 }
 EXPORTED_SYMBOLS = tuple(_PROTOS)
 UPB_PEER_HANDLE_BYTES = 64

@@ -102,7 +102,7 @@ struct ApplyArgs {
   const long long* steps_in;  // [4] global, encoder+value, land-use head, road head
   long long* steps_out;       // [4] written by block 0 (ping-pong with steps_in across calls)
   float lr, beta1, beta2, eps;
-  int clip_mode;
+  int clip_now;               // 1: two-group clip on this step (decided on the host: mode + first-step latch)
 };
 
 constexpr int AP_THREADS = 512;
@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(AP_THREADS) k_apply(const ApplyArgs a) {
   const float* st = a.grad + UPB_STAT_OFFSET;
   const bool live_lu = st[5] > 0.f, live_rd = st[6] > 0.f;
   const long long gstep = a.steps_in[0];
-  const bool do_clip = a.clip_mode == UPB_CLIP_ALWAYS || (a.clip_mode == UPB_CLIP_REFERENCE && gstep == 0);
+  const bool do_clip = a.clip_now != 0;
   float c_enc = 1.f, c_pol = 1.f, c_val = 1.f;
   if (do_clip) {
     float se = 0.f, sp = 0.f, sv = 0.f;

@@ -6,9 +6,11 @@
  * line per array; the objects of a large rollout buffer are cold in memory, so touching less matters), anything else
  * goes through the buffer protocol.  Host glue only: no CUDA.
  *
- *   pointer_table(states, out) -> -1 on success, or the index of the first state that needs the slow path
+ *   pointer_table(states, out, n_cap, e_cap) -> -1 on success, or the index of the first state that needs the slow path
  *     states : list/tuple of list/tuple of 9 objects exporting C-contiguous buffers
  *     out    : writable buffer of 9 * len(states) uint64
+ *     n_cap, e_cap : padded widths the packer will read; an array with a different element count raises ValueError
+ *                    (the packer trusts the pointers: a short array would be an out-of-bounds host read)
  */
 #define PY_SSIZE_T_CLEAN
 #include <Python.h>
@@ -32,10 +34,18 @@ static int kind_ok(const char* fmt, char want) {
   }
 }
 
+static int size_ok(int j, Py_ssize_t size, const Py_ssize_t want[9]) {
+  return j == 8 ? size >= 2 : size == want[j];     /* stage: 3 in the reference, the packer reads entries 0 and 1 */
+}
+
 static PyObject* pointer_table(PyObject* self, PyObject* args) {
   PyObject* states;
   Py_buffer out;
-  if (!PyArg_ParseTuple(args, "Ow*", &states, &out)) return NULL;
+  long n_cap = 0, e_cap = 0;
+  if (!PyArg_ParseTuple(args, "Ow*ll", &states, &out, &n_cap, &e_cap)) return NULL;
+  const Py_ssize_t want[9] = {52, (Py_ssize_t)n_cap * 23, (Py_ssize_t)e_cap * 2, 23, n_cap, e_cap, e_cap, n_cap, 3};
+  long bad_size_state = -1;
+  int bad_size_arr = -1;
   PyObject* seq = PySequence_Fast(states, "states must be a sequence");
   if (!seq) { PyBuffer_Release(&out); return NULL; }
   const Py_ssize_t count = PySequence_Fast_GET_SIZE(seq);
@@ -54,6 +64,7 @@ static PyObject* pointer_table(PyObject* self, PyObject* args) {
       PyObject* a = PySequence_Fast_GET_ITEM(st, j);
       if (PyArray_CheckExact(a)) {
         PyArrayObject* arr = (PyArrayObject*)a;
+        if (!size_ok(j, (Py_ssize_t)PyArray_SIZE(arr), want)) { bad_size_state = (long)i; bad_size_arr = j; bad = (long)i; break; }
         if (PyArray_TYPE(arr) == kTypeNum[j] && PyArray_IS_C_CONTIGUOUS(arr) && PyArray_ISNOTSWAPPED(arr)) {
           dst[9 * i + j] = (uint64_t)(uintptr_t)PyArray_DATA(arr);
           continue;
@@ -64,13 +75,22 @@ static PyObject* pointer_table(PyObject* self, PyObject* args) {
       Py_buffer v;
       if (PyObject_GetBuffer(a, &v, PyBUF_C_CONTIGUOUS | PyBUF_FORMAT) < 0) { PyErr_Clear(); bad = (long)i; break; }
       const int ok = v.itemsize == kItem[j] && kind_ok(v.format, kKind[j]);
+      const int sz_ok = v.itemsize > 0 && size_ok(j, v.len / v.itemsize, want);
       dst[9 * i + j] = (uint64_t)(uintptr_t)v.buf;
       PyBuffer_Release(&v);         /* the caller's list keeps the array alive */
+      if (!sz_ok) { bad_size_state = (long)i; bad_size_arr = j; bad = (long)i; break; }
       if (!ok) { bad = (long)i; break; }
     }
   }
   PyBuffer_Release(&out);
   Py_DECREF(seq);
+  if (bad_size_state >= 0) {
+    PyErr_Format(PyExc_ValueError,
+                 "state %ld, array %d: element count does not match the padded widths (n_cap=%ld, e_cap=%ld): expected "
+                 "52, n_cap*23, e_cap*2, 23, n_cap, e_cap, e_cap, n_cap, 3",
+                 bad_size_state, bad_size_arr, n_cap, e_cap);
+    return NULL;
+  }
   return PyLong_FromLong(bad);
 }
 

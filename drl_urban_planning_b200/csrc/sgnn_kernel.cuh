@@ -182,18 +182,20 @@ struct StepArgs {
   // the same launch, separated by grid barriers (cooperative launch: all CTAs are co-resident)
   int fuse_tail;
   float* params_rw;            // == params, writable
-  float* gsum;                 // [G_ROW]
   float* grad_out;             // [UPB_GRAD_STRIDE]
   float* adam_m;
   float* adam_v;
   const long long* steps_in;   // [4]
   long long* steps_out;        // [4]
-  unsigned int* gridbar;       // [3] two arrival counters + stage bits, zero between launches
+  unsigned int* gridbar;       // [8]: [0] cumulative arrival counter (never reset), [2], [3] stage bits by launch
+                               // parity, [6] sticky count of CTAs that gave up on a peer
+  unsigned int bar_target;     // value of gridbar[0] once every CTA of this launch has arrived
   float lr, beta1, beta2, adam_eps;
-  // multi-GPU fused tail (upb_peer_connect): the per-rank column sums are exchanged through peer memory (NVLink) inside
-  // the kernel.  xchg layout per rank (floats): [2 parities][G_ROW] sums, then [2][2][MAX_PEERS] u32: sequence flags | stage bits.
+  // exchange buffers of the fused tail (one GPU: world = 1, own buffer only; upb_peer_connect: all ranks', mapped over
+  // NVLink).  Layout per rank (floats): [2 parities][MAX_PEERS sources][G_ROW] sums, then u32 flags
+  // [2][MAX_PEERS][FLAG_STRIDE] = (sequence << 2) | stage bits of the source rank.
   int world, rank;
-  unsigned int seq;            // exchange sequence number of this step (same on all ranks, starts at 1)
+  unsigned int seq;            // sequence number of this fused step (same on all ranks, starts at 1)
   float* const* peers;         // device array [world] of the ranks' exchange buffers (own buffer at [rank])
   long long* stamps;   // optional [384]: [0,64) clock64() phase stamps, [64,224) busy cycles per CTA, [224,384) prologue cycles; of the first graph of CTA 0 (tools/phase_times.py)
 };
@@ -1749,7 +1751,58 @@ __device__ void graph_body(const StepArgs& a, const BlobHeader& hd, const GraphD
 }
 
 
-// ---- fused tail: gradient reduction, attention chain, Adam (see upb_ppo_step) ------------------------------------------
+// ---- fused tail: gradient reduction, (cross-GPU) exchange, attention chain, Adam (see upb_ppo_step) ----------------------
+// One code path for one GPU and for data-parallel ranks (one process per GPU, peers opened with CUDA IPC over NVLink /
+// NVSwitch).  The flat gradient row is cut into NSLICE slices of 128 columns; slice s is owned by CTA s % gridDim.x of
+// every rank.
+//   grid barrier (local)  : all graphs of all CTAs are done, the per-CTA partial rows are complete
+//   PUSH                  : the owner sums its slice over the local CTAs (fixed order) and STORES the 128 sums into
+//                           region [parity][src = this rank] of EVERY rank's exchange buffer (remote stores over NVLink,
+//                           fire and forget), then releases one flag per (destination rank, slice) carrying the step
+//                           sequence number and this rank's stage bits
+//   REDUCE + ADAM         : the owner polls the flags of ITS slice in its own (local) buffer until every rank has
+//                           delivered, adds the world contributions in rank order (local loads) and applies Adam to its
+//                           columns -- no second grid barrier, no serial publish, no remote loads, and a slice proceeds as
+//                           soon as it alone has arrived
+//   ATTENTION CHAIN       : the last CTA waits for the seven slices that hold the 816 "virtual" gradients of the composed
+//                           attention projections, chains them to the six real tensors and applies their Adam.
+// Same summation order on every rank -> bit-identical parameters everywhere without a broadcast.  Regions and flags are
+// double-buffered by step parity: a rank can be at most one step ahead of the slowest one (it needs that rank's flags of
+// the current step before its kernel can finish), so parity p is never rewritten while it is being read.
+constexpr int MAX_PEERS = 16;
+constexpr int SLICE = 128;
+constexpr int NSLICE = G_ROW / SLICE;            // 114
+static_assert(G_ROW % SLICE == 0, "slices tile the gradient row");
+constexpr int CHAIN_S0 = G_QC / SLICE;           // first / last slice holding virtual attention gradients
+constexpr int CHAIN_S1 = (G_STATS - 1) / SLICE;
+constexpr int FLAG_STRIDE = 128;                 // flag words per (parity, source rank)
+constexpr size_t XCHG_FLAGS = (size_t)2 * MAX_PEERS * G_ROW;                       // float offset of the flag words
+constexpr size_t XCHG_FLOATS = XCHG_FLAGS + (size_t)2 * MAX_PEERS * FLAG_STRIDE;   // whole buffer
+static_assert(NSLICE <= FLAG_STRIDE, "one flag word per slice");
+constexpr unsigned PEER_SPIN_LIMIT = 1u << 24;   // polls before a CTA gives up on a peer (seconds): the step's Adam update
+                                                 // is then SKIPPED by that CTA and the sticky counter gridbar[6] is bumped
+
+__device__ __forceinline__ float ld_relaxed(const float* p, bool sys) {
+  float v;
+  if (sys) asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  else asm volatile("ld.relaxed.gpu.global.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void st_relaxed(float* p, float v, bool sys) {
+  if (sys) asm volatile("st.relaxed.sys.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+  else asm volatile("st.relaxed.gpu.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire(const unsigned* p, bool sys) {
+  unsigned v;
+  if (sys) asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  else asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release(unsigned* p, unsigned v, bool sys) {
+  if (sys) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+  else asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 __device__ __forceinline__ void grid_arrive(unsigned int* ctr) {
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -1757,33 +1810,16 @@ __device__ __forceinline__ void grid_arrive(unsigned int* ctr) {
     atomicAdd(ctr, 1u);
   }
 }
+// the counter is never reset: the host passes the cumulative arrival count this launch ends at (wrap-safe compare)
 __device__ __forceinline__ void grid_wait(unsigned int* ctr, unsigned int target) {
   if (threadIdx.x == 0) {
     unsigned int v;
     do {
-      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr));
-    } while (v < target);
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+    } while ((int)(v - target) < 0);
     __threadfence();
   }
   __syncthreads();
-}
-
-// ---- cross-GPU exchange (one process per GPU, peers opened with CUDA IPC over NVLink / NVSwitch) ---------------------
-constexpr int MAX_PEERS = 16;
-constexpr int XCHG_FLAGS = 2 * G_ROW;          // float offset of the flag words inside an exchange buffer
-constexpr unsigned PEER_SPIN_LIMIT = 1u << 22; // polls before a rank gives up on a peer (seconds; flags the step invalid)
-__device__ __forceinline__ float ld_sys(const float* p) {
-  float v;
-  asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p));
-  return v;
-}
-__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
-  return v;
-}
-__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
 // torch.optim.Adam on one element with torch's operation order (same arithmetic as k_apply; no clipping here).
@@ -1800,16 +1836,29 @@ __device__ __forceinline__ void adam_elem(const StepArgs& a, int i, float g, flo
 }
 
 // Everything that does not depend on other CTAs' results is fetched or computed BEFORE the barrier it would otherwise
-// follow, so the serial part after each barrier is short.
+// follow, so the serial part after the barrier is short.
 __device__ void fused_tail(const StepArgs& a, float* smem, unsigned stage_bits) {
-  constexpr int COLS = 128;                         // columns per CTA and pass, 4 threads per column
   const int tid = threadIdx.x;
   const int nparts = gridDim.x;
+  const int world = a.world, me = a.rank;
+  const bool sys = world > 1;                       // flag / data scope: peers over NVLink need system scope
+  const unsigned par = a.seq & 1u;
+  const bool chain_cta = blockIdx.x == gridDim.x - 1;
   __shared__ float sh_adam[12];                     // [seg][live ? 1 : 0][step_size, sqrt(bc2)]
   __shared__ long long sh_steps[6];
+  __shared__ unsigned sh_bits;                      // OR of the ranks' stage bits (carried by the flags)
+  __shared__ int sh_timeout;
+  __shared__ float* sh_push[MAX_PEERS];             // region [par][src = me] of every rank's buffer
 #define UPB_TSTAMP(ID) do { if (a.stamps != nullptr && blockIdx.x == 0 && threadIdx.x == 0) a.stamps[ID] = clock64(); } while (0)
   UPB_TSTAMP(40);
-  if (tid == 0 && stage_bits) atomicOr(a.gridbar + 2, stage_bits);     // which policy heads this CTA's graphs used
+  float* const mine = a.peers[me];
+  const float* const pull = mine + (size_t)par * MAX_PEERS * G_ROW;        // [src][G_ROW] contributions delivered to me
+  const unsigned* const myflags = reinterpret_cast<const unsigned*>(mine + XCHG_FLAGS) + (size_t)par * MAX_PEERS * FLAG_STRIDE;
+  if (tid < world) sh_push[tid] = a.peers[tid] + ((size_t)par * MAX_PEERS + me) * G_ROW;
+  if (tid == 32) { sh_timeout = 0; sh_bits = 0u; }
+  if (tid == 0 && stage_bits) atomicOr(a.gridbar + 2 + par, stage_bits);   // which policy heads this CTA's graphs used
+  if (tid == 1 && blockIdx.x == 0) a.gridbar[2 + (par ^ 1u)] = 0u;         // the NEXT launch's word (the previous launch,
+                                                                           // which used it, has completed)
   if (tid < 6) {      // Adam bias corrections of the three segments, for "head live" and "head skipped"
     const int seg = tid >> 1, live = tid & 1;
     const long long stp = a.steps_in[1 + seg] + live;
@@ -1819,13 +1868,13 @@ __device__ void fused_tail(const StepArgs& a, float* smem, unsigned stage_bits) 
     sh_adam[tid * 2 + 1] = (float)sqrt(bc2);
     sh_steps[tid] = stp;
   }
-  // this thread's column of the first pass: its moments / parameter do not depend on the reduction
-  const int col0 = blockIdx.x * COLS + (tid >> 2), part = tid & 3;
+  // this thread's column of the first owned slice: its moments / parameter do not depend on the reduction
+  const int col0 = blockIdx.x * SLICE + (tid >> 2), part = tid & 3;
   const bool attn0 = (col0 >= P_MHA_IN_W && col0 < P_MHA_OUT_W) || (col0 >= P_ATT_Q_W && col0 < P_LU_W0);
   const bool real0 = part == 0 && col0 < NUM_PARAMS && !attn0;
   float pm = 0.f, pv = 0.f, pp = 0.f;
   if (real0) { pm = a.adam_m[col0]; pv = a.adam_v[col0]; pp = a.params_rw[col0]; }
-  // CTA 0 also prefetches what the attention chain needs from the (still old) parameters
+  // the chain CTA also prefetches what the attention chain needs from the (still old) parameters
   float* sG = smem;                 // Qc | qbc | Kc | Vc | vbc gradients [816]
   float* sWin = sG + 816;           // in_proj_weight [768]
   float* sW3 = sWin + 768;          // Wq | Wk | Wv [768]
@@ -1835,7 +1884,7 @@ __device__ void fused_tail(const StepArgs& a, float* smem, unsigned stage_bits) 
   const int pB[3] = {P_ATT_Q_B, P_ATT_K_B, P_ATT_V_B};
   float cm[4], cv[4], cp[4];
   int cdst[4];
-  if (blockIdx.x == 0) {
+  if (chain_cta) {
     const float* P = a.params_rw;
     for (int i = tid; i < 768; i += NT) sWin[i] = P[P_MHA_IN_W + i];
     if (tid < 256) { sW3[tid] = P[P_ATT_Q_W + tid]; sW3[256 + tid] = P[P_ATT_K_W + tid]; sW3[512 + tid] = P[P_ATT_V_W + tid]; }
@@ -1853,20 +1902,17 @@ __device__ void fused_tail(const StepArgs& a, float* smem, unsigned stage_bits) 
     }
   }
   grid_arrive(a.gridbar);                           // all graphs of all CTAs are done, gpart rows are complete
-  grid_wait(a.gridbar, gridDim.x);
+  grid_wait(a.gridbar, a.bar_target);
   UPB_TSTAMP(41);
-  unsigned bits;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(bits) : "l"(a.gridbar + 2));
-  const bool live_lu = bits & 1u, live_rd = bits & 2u;
-  if (blockIdx.x == 0 && tid < 4) {
-    // step counters: [0] global, [1] encoder+value, [2] land-use head, [3] road head
-    a.steps_out[tid] = tid == 0 ? a.steps_in[0] + 1
-                                : sh_steps[(tid - 1) * 2 + (tid == 1 ? 1 : (tid == 2 ? (live_lu ? 1 : 0) : (live_rd ? 1 : 0)))];
-  }
-  for (int c0 = blockIdx.x * COLS; c0 < G_ROW; c0 += gridDim.x * COLS) {
-    const int col = c0 + (tid >> 2);
-    float s = 0.f;
-    if (col < G_ROW) {      // rows part, part+4, ...: eight loads in flight per thread, fixed summation order
+  unsigned mybits;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(mybits) : "l"(a.gridbar + 2 + par) : "memory");
+  const unsigned flagword = (a.seq << 2) | (mybits & 3u);
+
+  // ---- PUSH: local column sums of the owned slices -> every rank's buffer
+  for (int sl = blockIdx.x; sl < NSLICE; sl += gridDim.x) {
+    const int col = sl * SLICE + (tid >> 2);
+    float s;
+    {       // rows part, part+4, ...: eight loads in flight per thread, fixed summation order
       const float* src = a.gpart + col;
       float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, s4 = 0.f, s5 = 0.f, s6 = 0.f, s7 = 0.f;
       int r = part;
@@ -1880,9 +1926,41 @@ __device__ void fused_tail(const StepArgs& a, float* smem, unsigned stage_bits) 
       s = ((s0 + s1) + (s2 + s3)) + ((s4 + s5) + (s6 + s7));
     }
     s += __shfl_xor_sync(0xffffffffu, s, 1);
-    s += __shfl_xor_sync(0xffffffffu, s, 2);
-    if (part == 0 && col < G_ROW) {
-      a.gsum[col] = s;
+    s += __shfl_xor_sync(0xffffffffu, s, 2);         // all four lanes of the column hold the sum
+    for (int r = part; r < world; r += 4) st_relaxed(sh_push[r] + col, s, sys);     // lane p serves ranks p, p+4, ...
+  }
+  __syncthreads();                                   // this CTA's pushes are issued (ordered before the releases below)
+  {
+    const int nown = (NSLICE - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    for (int idx = tid; idx < world * nown; idx += NT) {
+      const int r = idx % world, sl = blockIdx.x + (idx / world) * gridDim.x;
+      unsigned* f = reinterpret_cast<unsigned*>(a.peers[r] + XCHG_FLAGS) + ((size_t)par * MAX_PEERS + me) * FLAG_STRIDE + sl;
+      if (sys) __threadfence_system(); else __threadfence();
+      st_release(f, flagword, sys);
+    }
+  }
+  UPB_TSTAMP(42);
+
+  // ---- REDUCE + ADAM per owned slice
+  for (int sl = blockIdx.x; sl < NSLICE; sl += gridDim.x) {
+    if (tid < world) {                               // every rank (this one included) has delivered this slice
+      unsigned polls = 0, f;
+      while ((int)(((f = ld_acquire(myflags + (size_t)tid * FLAG_STRIDE + sl, sys)) >> 2) - a.seq) < 0) {
+        if (++polls >= PEER_SPIN_LIMIT) { sh_timeout = 1; break; }
+      }
+      if (f & 3u) atomicOr(&sh_bits, f & 3u);
+    }
+    __syncthreads();
+    const bool live_lu = sh_bits & 1u, live_rd = sh_bits & 2u;
+    const bool dead = sh_timeout != 0;
+    const int col = sl * SLICE + (tid >> 2);
+    if (part == 0) {
+      float v[MAX_PEERS];
+#pragma unroll
+      for (int p = 0; p < MAX_PEERS; ++p) v[p] = p < world ? ld_relaxed(pull + (size_t)p * G_ROW + col, sys) : 0.f;
+      float s = v[0];
+#pragma unroll
+      for (int p = 1; p < MAX_PEERS; ++p) if (p < world) s += v[p];         // rank order: identical on every rank
       const bool attn = (col >= P_MHA_IN_W && col < P_MHA_OUT_W) || (col >= P_ATT_Q_W && col < P_LU_W0);
       if (col < NUM_PARAMS && !attn) {
         a.grad_out[col] = s;
@@ -1890,8 +1968,8 @@ __device__ void fused_tail(const StepArgs& a, float* smem, unsigned stage_bits) 
         bool live = true;
         if (col >= P_LU_W0 && col < P_RD_W0) { seg = 1; live = live_lu; }
         else if (col >= P_RD_W0 && col < POLICY_END) { seg = 2; live = live_rd; }
-        if (live) {
-          if (col != col0) { pm = a.adam_m[col]; pv = a.adam_v[col]; pp = a.params_rw[col]; }     // later passes (small grids)
+        if (live && !dead) {
+          if (col != col0) { pm = a.adam_m[col]; pv = a.adam_v[col]; pp = a.params_rw[col]; }     // later slices (small grids)
           adam_elem(a, col, s, pm, pv, pp, sh_adam[(seg * 2 + 1) * 2], sh_adam[(seg * 2 + 1) * 2 + 1]);
         }
       } else if (col >= NUM_PARAMS && col < UPB_STAT_OFFSET) {
@@ -1900,14 +1978,53 @@ __device__ void fused_tail(const StepArgs& a, float* smem, unsigned stage_bits) 
       if (col >= G_STATS && col < G_STATS + 8) a.grad_out[UPB_STAT_OFFSET + (col - G_STATS)] = s;
       if (col >= G_STATS + 8 && col < G_STATS + UPB_STAT_COUNT) a.grad_out[UPB_STAT_OFFSET + (col - G_STATS)] = 0.f;
     }
+    __syncthreads();                                 // sh_bits / sh_timeout are read before the next slice's polls
   }
-  UPB_TSTAMP(42);
-  grid_arrive(a.gridbar + 1);                       // this CTA's columns of gsum are written
-  if (blockIdx.x != 0) return;
-  grid_wait(a.gridbar + 1, gridDim.x);
   UPB_TSTAMP(43);
-  // CTA 0: chain the composed-projection gradients to the six attention tensors (old parameter values), then their Adam
-  for (int i = tid; i < 816; i += NT) sG[i] = __ldcg(a.gsum + G_QC + i);
+  if (!chain_cta) {
+    if (tid == 0 && sh_timeout) atomicAdd(a.gridbar + 6, 1u);
+    return;
+  }
+
+  // ---- ATTENTION CHAIN (last CTA): the virtual gradients of all ranks, chained to the six attention tensors, Adam
+  {
+    constexpr int NCH = CHAIN_S1 - CHAIN_S0 + 1;
+    if (tid < world * NCH) {
+      const int r = tid % world, sl = CHAIN_S0 + tid / world;
+      unsigned polls = 0, f;
+      while ((int)(((f = ld_acquire(myflags + (size_t)r * FLAG_STRIDE + sl, sys)) >> 2) - a.seq) < 0) {
+        if (++polls >= PEER_SPIN_LIMIT) { sh_timeout = 1; break; }
+      }
+      if (f & 3u) atomicOr(&sh_bits, f & 3u);
+    }
+    __syncthreads();
+  }
+  const bool dead = sh_timeout != 0;
+  if (tid < 4) {
+    // step counters: [0] global, [1] encoder+value, [2] land-use head, [3] road head
+    const bool live_lu = sh_bits & 1u, live_rd = sh_bits & 2u;
+    if (!dead)
+      a.steps_out[tid] = tid == 0 ? a.steps_in[0] + 1
+                                  : sh_steps[(tid - 1) * 2 + (tid == 1 ? 1 : (tid == 2 ? (live_lu ? 1 : 0) : (live_rd ? 1 : 0)))];
+    else
+      a.steps_out[tid] = a.steps_in[tid];
+  }
+  {   // all loads of a thread are issued before the first use
+    float v0[MAX_PEERS], v1[MAX_PEERS];
+#pragma unroll
+    for (int p = 0; p < MAX_PEERS; ++p) {
+      v0[p] = 0.f; v1[p] = 0.f;
+      if (p < world) {
+        v0[p] = ld_relaxed(pull + (size_t)p * G_ROW + G_QC + tid, sys);
+        if (tid + NT < 816) v1[p] = ld_relaxed(pull + (size_t)p * G_ROW + G_QC + tid + NT, sys);
+      }
+    }
+    float s0 = v0[0], s1 = v1[0];
+#pragma unroll
+    for (int p = 1; p < MAX_PEERS; ++p) if (p < world) { s0 += v0[p]; s1 += v1[p]; }
+    sG[tid] = s0;
+    if (tid + NT < 816) sG[tid + NT] = s1;
+  }
   __syncthreads();
   if (tid < 256) {
     const int r = tid >> 4, c = tid & 15;
@@ -1945,223 +2062,11 @@ __device__ void fused_tail(const StepArgs& a, float* smem, unsigned stage_bits) 
     if (i < 1632) {
       const float g = sOut[i];
       a.grad_out[cdst[j]] = g;
-      adam_elem(a, cdst[j], g, cm[j], cv[j], cp[j], sh_adam[2], sh_adam[3]);     // segment 0 (encoder), live
+      if (!dead) adam_elem(a, cdst[j], g, cm[j], cv[j], cp[j], sh_adam[2], sh_adam[3]);     // segment 0 (encoder), live
     }
   }
-  __syncthreads();
-  if (tid == 0) { a.gridbar[0] = 0u; a.gridbar[1] = 0u; a.gridbar[2] = 0u; }   // all CTAs are past both barriers
+  if (tid == 0 && dead) atomicAdd(a.gridbar + 6, 1u);
   UPB_TSTAMP(44);
-}
-
-// Multi-GPU variant of the fused tail (a.world > 1): data-parallel ranks, each with its own shard of the minibatch.
-//   barrier 1 (local)  -> every CTA sums its 128 columns over the local CTAs into this rank's exchange buffer
-//   barrier 2 (local)  -> CTA 0 publishes this rank's stage bits and "rank r, step seq ready" into every rank's flag rows
-//                         (st.release.sys over NVLink)
-//   every CTA polls its OWN rank's flag row (local memory) until all ranks are ready, then sums its columns over the
-//   ranks in rank order (peer loads) and applies Adam; CTA 0 also sums the 816 virtual attention gradients itself and
-//   chains them.  Same summation order on every rank -> bit-identical parameters everywhere, no NCCL call, one launch
-//   per optimiser step.  The exchange buffer is double-buffered by step parity: a rank can only be one step ahead of
-//   the slowest one (it needs that rank's flag of the current step), so parity p is never rewritten while it is read.
-__device__ void fused_tail_peers(const StepArgs& a, float* smem, unsigned stage_bits) {
-  constexpr int COLS = 128;
-  const int tid = threadIdx.x;
-  const int nparts = gridDim.x;
-  const int world = a.world;
-  __shared__ float sh_adam[12];
-  __shared__ long long sh_steps[6];
-  __shared__ int sh_live[2];
-  __shared__ int sh_timeout;
-  __shared__ const float* sh_peer[MAX_PEERS];
-  const unsigned par = a.seq & 1u;
-  if (tid < world) sh_peer[tid] = a.peers[tid] + (size_t)par * G_ROW;
-  if (tid == 32) { sh_timeout = 0; sh_live[0] = 0; sh_live[1] = 0; }
-  if (tid < 6) {
-    const int seg = tid >> 1, live = tid & 1;
-    const long long stp = a.steps_in[1 + seg] + live;
-    const double bc1 = 1.0 - ipow((double)a.beta1, stp > 0 ? stp : 1);
-    const double bc2 = 1.0 - ipow((double)a.beta2, stp > 0 ? stp : 1);
-    sh_adam[tid * 2 + 0] = (float)((double)a.lr / bc1);
-    sh_adam[tid * 2 + 1] = (float)sqrt(bc2);
-    sh_steps[tid] = stp;
-  }
-  float* xself = a.peers[a.rank] + (size_t)par * G_ROW;
-  if (tid == 0 && stage_bits) atomicOr(a.gridbar + 2, stage_bits);     // which policy heads this CTA's graphs used
-  const int col0 = blockIdx.x * COLS + (tid >> 2), part = tid & 3;
-  const bool attn0 = (col0 >= P_MHA_IN_W && col0 < P_MHA_OUT_W) || (col0 >= P_ATT_Q_W && col0 < P_LU_W0);
-  const bool real0 = part == 0 && col0 < NUM_PARAMS && !attn0;
-  float pm = 0.f, pv = 0.f, pp = 0.f;
-  if (real0) { pm = a.adam_m[col0]; pv = a.adam_v[col0]; pp = a.params_rw[col0]; }
-  float* sG = smem;
-  float* sWin = sG + 816;
-  float* sW3 = sWin + 768;
-  float* sB = sW3 + 768;
-  float* sOut = sB + 48;
-  const int pW[3] = {P_ATT_Q_W, P_ATT_K_W, P_ATT_V_W};
-  const int pB[3] = {P_ATT_Q_B, P_ATT_K_B, P_ATT_V_B};
-  float cm[4], cv[4], cp[4];
-  int cdst[4];
-  if (blockIdx.x == 0) {
-    const float* P = a.params_rw;
-    for (int i = tid; i < 768; i += NT) sWin[i] = P[P_MHA_IN_W + i];
-    if (tid < 256) { sW3[tid] = P[P_ATT_Q_W + tid]; sW3[256 + tid] = P[P_ATT_K_W + tid]; sW3[512 + tid] = P[P_ATT_V_W + tid]; }
-    if (tid < 16) { sB[tid] = P[P_ATT_Q_B + tid]; sB[16 + tid] = P[P_ATT_K_B + tid]; sB[32 + tid] = P[P_ATT_V_B + tid]; }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int i = tid + j * NT;
-      int dst = 0;
-      if (i < 768) dst = pW[i >> 8] + (i & 255);
-      else if (i < 1536) dst = P_MHA_IN_W + (i - 768);
-      else if (i < 1584) dst = pB[(i - 1536) >> 4] + ((i - 1536) & 15);
-      else if (i < 1632) dst = P_MHA_IN_B + (i - 1584);
-      cdst[j] = dst;
-      if (i < 1632) { cm[j] = a.adam_m[dst]; cv[j] = a.adam_v[dst]; cp[j] = P[dst]; }
-    }
-  }
-  grid_arrive(a.gridbar);
-  grid_wait(a.gridbar, gridDim.x);
-  // local column sums -> this rank's exchange buffer
-  for (int c0 = blockIdx.x * COLS; c0 < G_ROW; c0 += gridDim.x * COLS) {
-    const int col = c0 + (tid >> 2);
-    float s = 0.f;
-    if (col < G_ROW) {
-      const float* src = a.gpart + col;
-      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, s4 = 0.f, s5 = 0.f, s6 = 0.f, s7 = 0.f;
-      int r = part;
-      for (; r + 28 < nparts; r += 32) {
-        s0 += __ldcg(src + (size_t)r * G_ROW);        s1 += __ldcg(src + (size_t)(r + 4) * G_ROW);
-        s2 += __ldcg(src + (size_t)(r + 8) * G_ROW);  s3 += __ldcg(src + (size_t)(r + 12) * G_ROW);
-        s4 += __ldcg(src + (size_t)(r + 16) * G_ROW); s5 += __ldcg(src + (size_t)(r + 20) * G_ROW);
-        s6 += __ldcg(src + (size_t)(r + 24) * G_ROW); s7 += __ldcg(src + (size_t)(r + 28) * G_ROW);
-      }
-      for (; r < nparts; r += 4) s0 += __ldcg(src + (size_t)r * G_ROW);
-      s = ((s0 + s1) + (s2 + s3)) + ((s4 + s5) + (s6 + s7));
-    }
-    s += __shfl_xor_sync(0xffffffffu, s, 1);
-    s += __shfl_xor_sync(0xffffffffu, s, 2);
-    if (part == 0 && col < G_ROW) __stcg(xself + col, s);
-  }
-  grid_arrive(a.gridbar + 1);
-  if (blockIdx.x == 0) {
-    grid_wait(a.gridbar + 1, gridDim.x);            // every column of this rank is in its exchange buffer
-    if (tid < world) {                              // publish to rank `tid`: this rank's stage bits, then the step flag
-      unsigned bits;
-      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(bits) : "l"(a.gridbar + 2));
-      unsigned* row = reinterpret_cast<unsigned*>(a.peers[tid] + XCHG_FLAGS) + par * 2 * MAX_PEERS;
-      __threadfence_system();
-      asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(row + MAX_PEERS + a.rank), "r"(bits) : "memory");
-      st_release_sys(row + a.rank, a.seq);
-    }
-  }
-  if (tid < world) {                                // all ranks (this one included) have published this step
-    const unsigned* row = reinterpret_cast<const unsigned*>(a.peers[a.rank] + XCHG_FLAGS) + par * 2 * MAX_PEERS;
-    unsigned polls = 0;
-    while ((int)(ld_acquire_sys(row + tid) - a.seq) < 0) {
-      if (++polls >= PEER_SPIN_LIMIT) { sh_timeout = 1; break; }
-    }
-    unsigned bits;
-    asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(bits) : "l"(row + MAX_PEERS + tid));
-    if (bits & 1u) sh_live[0] = 1;                  // benign race: every writer stores 1
-    if (bits & 2u) sh_live[1] = 1;
-    __threadfence_system();
-  }
-  __syncthreads();
-  const bool live_lu = sh_live[0], live_rd = sh_live[1];
-  if (blockIdx.x == 0 && tid < 4) {
-    a.steps_out[tid] = tid == 0 ? a.steps_in[0] + 1
-                                : sh_steps[(tid - 1) * 2 + (tid == 1 ? 1 : (tid == 2 ? (live_lu ? 1 : 0) : (live_rd ? 1 : 0)))];
-  }
-  // All peer loads of a thread are issued before the first use: one NVLink round trip per phase, not one per rank.
-  float att0[MAX_PEERS], att1[MAX_PEERS];           // CTA 0: the ranks' virtual attention gradients tid and tid + NT
-  if (blockIdx.x == 0) {
-#pragma unroll
-    for (int p = 0; p < MAX_PEERS; ++p) {
-      att0[p] = 0.f; att1[p] = 0.f;
-      if (p < world) {
-        att0[p] = ld_sys(sh_peer[p] + G_QC + tid);
-        if (tid + NT < 816) att1[p] = ld_sys(sh_peer[p] + G_QC + tid + NT);
-      }
-    }
-  }
-  for (int c0 = blockIdx.x * COLS; c0 < G_ROW; c0 += gridDim.x * COLS) {
-    const int col = c0 + (tid >> 2);
-    if (part == 0 && col < G_ROW) {
-      float v[MAX_PEERS];
-#pragma unroll
-      for (int p = 0; p < MAX_PEERS; ++p) v[p] = p < world ? ld_sys(sh_peer[p] + col) : 0.f;
-      float s = 0.f;
-#pragma unroll
-      for (int p = 0; p < MAX_PEERS; ++p) s += v[p];                        // rank order: identical on every rank
-      if (col == G_STATS + 7 && sh_timeout) s += 1.f;                       // a peer never showed up: step is invalid
-      a.gsum[col] = s;
-      const bool attn = (col >= P_MHA_IN_W && col < P_MHA_OUT_W) || (col >= P_ATT_Q_W && col < P_LU_W0);
-      if (col < NUM_PARAMS && !attn) {
-        a.grad_out[col] = s;
-        int seg = 0;
-        bool live = true;
-        if (col >= P_LU_W0 && col < P_RD_W0) { seg = 1; live = live_lu; }
-        else if (col >= P_RD_W0 && col < POLICY_END) { seg = 2; live = live_rd; }
-        if (live) {
-          if (col != col0) { pm = a.adam_m[col]; pv = a.adam_v[col]; pp = a.params_rw[col]; }
-          adam_elem(a, col, s, pm, pv, pp, sh_adam[(seg * 2 + 1) * 2], sh_adam[(seg * 2 + 1) * 2 + 1]);
-        }
-      } else if (col >= NUM_PARAMS && col < UPB_STAT_OFFSET) {
-        a.grad_out[col] = 0.f;
-      }
-      if (col >= G_STATS && col < G_STATS + 8) a.grad_out[UPB_STAT_OFFSET + (col - G_STATS)] = s;
-      if (col >= G_STATS + 8 && col < G_STATS + UPB_STAT_COUNT) a.grad_out[UPB_STAT_OFFSET + (col - G_STATS)] = 0.f;
-    }
-  }
-  if (blockIdx.x != 0) return;
-  // CTA 0: virtual attention gradients summed over the ranks, chained to the six attention tensors, then their Adam
-  {
-    float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-    for (int p = 0; p < MAX_PEERS; ++p) { s0 += att0[p]; s1 += att1[p]; }
-    sG[tid] = s0;
-    if (tid + NT < 816) sG[tid + NT] = s1;
-  }
-  __syncthreads();
-  if (tid < 256) {
-    const int r = tid >> 4, c = tid & 15;
-    const int gC[3] = {0, 272, 528};
-    const int gB[3] = {256, -1, 784};
-#pragma unroll
-    for (int s3 = 0; s3 < 3; ++s3) {
-      const float* Win = sWin + s3 * 256;
-      const float* gc = sG + gC[s3];
-      const float* W = sW3 + s3 * 256;
-      float ga = 0.f, gb = 0.f;
-#pragma unroll
-      for (int rr = 0; rr < 16; ++rr) {
-        ga = fmaf(Win[rr * 16 + r], gc[rr * 16 + c], ga);
-        gb = fmaf(gc[r * 16 + rr], W[c * 16 + rr], gb);
-      }
-      if (gB[s3] >= 0) gb = fmaf(sG[gB[s3] + r], sB[s3 * 16 + c], gb);
-      sOut[s3 * 256 + tid] = ga;
-      sOut[768 + s3 * 256 + tid] = gb;
-      if (tid < 16) {
-        float b1 = 0.f, b2 = 0.f;
-        if (gB[s3] >= 0) {
-          for (int rr = 0; rr < 16; ++rr) b1 = fmaf(Win[rr * 16 + tid], sG[gB[s3] + rr], b1);
-          b2 = sG[gB[s3] + tid];
-        }
-        sOut[1536 + s3 * 16 + tid] = b1;
-        sOut[1584 + s3 * 16 + tid] = b2;
-      }
-    }
-  }
-  __syncthreads();
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int i = tid + j * NT;
-    if (i < 1632) {
-      const float g = sOut[i];
-      a.grad_out[cdst[j]] = g;
-      adam_elem(a, cdst[j], g, cm[j], cv[j], cp[j], sh_adam[2], sh_adam[3]);
-    }
-  }
-  __syncthreads();
-  if (tid == 0) { a.gridbar[0] = 0u; a.gridbar[1] = 0u; a.gridbar[2] = 0u; }   // every CTA has arrived at both barriers
 }
 
 template <bool TRAIN>
@@ -2215,10 +2120,7 @@ __global__ void __launch_bounds__(NT, 1) k_sgnn(const __grid_constant__ StepArgs
   }
   if (a.stamps && threadIdx.x == 0 && blockIdx.x < 160) a.stamps[64 + blockIdx.x] = clock64() - t_cta0;           // CTA busy time
   if constexpr (TRAIN) {
-    if (a.fuse_tail) {
-      if (a.world > 1) fused_tail_peers(a, smem, stage_bits);
-      else fused_tail(a, smem, stage_bits);
-    }
+    if (a.fuse_tail) fused_tail(a, smem, stage_bits);
   }
 }
 

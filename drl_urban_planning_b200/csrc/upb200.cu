@@ -22,7 +22,7 @@ struct upb_ctx {
   int num_sms = 0;
   int grid = 0;
   float* gpart = nullptr;       // [grid][G_ROW]
-  float* gsum = nullptr;        // [G_ROW]
+  float* gsum = nullptr;        // [G_ROW] (two-call path: k_reduce_finish)
   float* scratch = nullptr;     // [grid][scratch_stride]
   size_t scratch_stride = 0;
   float* adam_m = nullptr;
@@ -30,8 +30,10 @@ struct upb_ctx {
   long long* steps = nullptr;   // device [2][4] ping-pong step counters
   int steps_cur = 0;
   unsigned int* ticket = nullptr;
-  unsigned int* gridbar = nullptr;   // [2] grid-barrier counters of the fused tail
+  unsigned int* gridbar = nullptr;   // [8] fused tail: cumulative arrival counter, stage bits by parity, peer-timeout count
+  unsigned int bar_total = 0;        // arrivals at gridbar[0] so far (the counter is never reset)
   int64_t host_steps = 0;            // optimiser steps applied so far (mirrors the device counter)
+  bool clip_armed = true;            // UPB_CLIP_REFERENCE: the next step is the process's first one and clips
   int coop = 0;                      // cooperative launch supported
   float* host_pinned = nullptr; // [UPB_STAT_COUNT] pinned staging for upb_read_losses
   int64_t launches = 0;
@@ -40,7 +42,8 @@ struct upb_ctx {
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
   size_t prof_used = 0;
   // multi-GPU fused step (upb_peer_export / upb_peer_connect)
-  float* xchg = nullptr;             // this rank's exchange buffer: [2][G_ROW] sums + [2][2][MAX_PEERS] flags | stage bits
+  float* xchg = nullptr;             // this rank's exchange buffer (sgnn_kernel.cuh: XCHG_FLOATS): slice sums by
+                                     // [parity][source rank], then the per-slice flags
   int world = 1, rank = 0;
   unsigned int peer_seq = 0;
   std::vector<void*> peer_ptrs;      // host copy: exchange buffers of all ranks (own at [rank])
@@ -99,6 +102,10 @@ void prof_end(upb_ctx* ctx, cudaStream_t s, bool on) {
   if (!on) return;
   cudaEventRecord(ctx->prof_events[ctx->prof_used].second, s);
   ctx->prof_used += 1;
+}
+
+bool clip_now(const upb_ctx* ctx) {
+  return ctx->cfg.clip_mode == UPB_CLIP_ALWAYS || (ctx->cfg.clip_mode == UPB_CLIP_REFERENCE && ctx->clip_armed);
 }
 
 StepArgs base_args(upb_ctx* ctx, const void* blob, const int32_t* ids, int count, const float* params,
@@ -170,8 +177,16 @@ extern "C" int upb_create(const upb_config* cfg, upb_ctx** out) {
   UPB_CUDA_F(cudaMalloc(&ctx->steps, sizeof(long long) * 8));
   UPB_CUDA_F(cudaMalloc(&ctx->ticket, sizeof(unsigned int)));
   UPB_CUDA_F(cudaMemset(ctx->ticket, 0, sizeof(unsigned int)));
-  UPB_CUDA_F(cudaMalloc(&ctx->gridbar, 4 * sizeof(unsigned int)));
-  UPB_CUDA_F(cudaMemset(ctx->gridbar, 0, 4 * sizeof(unsigned int)));
+  UPB_CUDA_F(cudaMalloc(&ctx->gridbar, 8 * sizeof(unsigned int)));
+  UPB_CUDA_F(cudaMemset(ctx->gridbar, 0, 8 * sizeof(unsigned int)));
+  UPB_CUDA_F(cudaMalloc(&ctx->xchg, sizeof(float) * XCHG_FLOATS));
+  UPB_CUDA_F(cudaMemset(ctx->xchg, 0, sizeof(float) * XCHG_FLOATS));
+  UPB_CUDA_F(cudaMalloc(&ctx->peers_dev, sizeof(float*) * MAX_PEERS));
+  {
+    float* self[MAX_PEERS] = {};
+    self[0] = ctx->xchg;                 // one GPU: rank 0 of a world of 1
+    UPB_CUDA_F(cudaMemcpy(ctx->peers_dev, self, sizeof(self), cudaMemcpyHostToDevice));
+  }
   UPB_CUDA_F(cudaDeviceGetAttribute(&ctx->coop, cudaDevAttrCooperativeLaunch, cfg->device));
   UPB_CUDA_F(cudaMemset(ctx->adam_m, 0, sizeof(float) * NUM_PARAMS));
   UPB_CUDA_F(cudaMemset(ctx->adam_v, 0, sizeof(float) * NUM_PARAMS));
@@ -285,7 +300,8 @@ extern "C" int upb_apply(upb_ctx* ctx, float* params, const float* grad, void* s
   a.beta1 = ctx->cfg.beta1;
   a.beta2 = ctx->cfg.beta2;
   a.eps = ctx->cfg.adam_eps;
-  a.clip_mode = ctx->cfg.clip_mode;
+  a.clip_now = clip_now(ctx) ? 1 : 0;
+  ctx->clip_armed = false;
   k_apply<<<AP_BLOCKS, AP_THREADS, 0, (cudaStream_t)stream>>>(a);
   ctx->launches += 1;
   UPB_CUDA(cudaGetLastError());
@@ -297,13 +313,12 @@ extern "C" int upb_ppo_step(upb_ctx* ctx, const void* blob_dev, const int32_t* i
                             const float* fixed_log_probs, const float* exps, float inv_batch, float inv_ind,
                             float* grad_out, void* stream) {
   if (int rc = check_ctx(ctx, "ppo_step")) return rc;
-  const bool clip_now = ctx->cfg.clip_mode == UPB_CLIP_ALWAYS ||
-                        (ctx->cfg.clip_mode == UPB_CLIP_REFERENCE && ctx->host_steps == 0);
+  const bool clip_step = clip_now(ctx);
   if (ctx->world > 1) {
-    if (clip_now || !ctx->coop)
+    if (clip_step || !ctx->coop)
       return set_error(UPB_ERR_ARG, "ppo_step: peers are connected and this step clips gradients; use upb_ppo_grad + "
                                     "all-reduce + upb_apply for it (upb_next_step_fused() == 0)");
-  } else if (clip_now || !ctx->coop || count <= 0) {      // clipping needs a grid-wide norm first: use the two-call path
+  } else if (clip_step || !ctx->coop || count <= 0) {      // clipping needs a grid-wide norm first: use the two-call path
     int rc = upb_ppo_grad(ctx, blob_dev, ids, count, params, actions, advantages, returns, fixed_log_probs, exps,
                           inv_batch, inv_ind, grad_out, stream);
     if (rc != UPB_OK) return rc;
@@ -321,7 +336,6 @@ extern "C" int upb_ppo_step(upb_ctx* ctx, const void* blob_dev, const int32_t* i
   a.inv_ind = inv_ind;
   a.fuse_tail = 1;
   a.params_rw = params;
-  a.gsum = ctx->gsum;
   a.grad_out = grad_out;
   a.adam_m = ctx->adam_m;
   a.adam_v = ctx->adam_v;
@@ -334,9 +348,11 @@ extern "C" int upb_ppo_step(upb_ctx* ctx, const void* blob_dev, const int32_t* i
   a.adam_eps = ctx->cfg.adam_eps;
   a.world = ctx->world;
   a.rank = ctx->rank;
-  a.seq = ctx->world > 1 ? ++ctx->peer_seq : 0u;
+  a.seq = ++ctx->peer_seq;
   a.peers = ctx->peers_dev;
   const int grid = count < 1 ? 1 : (count < ctx->grid ? count : ctx->grid);     // an empty shard still takes part in the exchange
+  ctx->bar_total += (unsigned int)grid;
+  a.bar_target = ctx->bar_total;
   void* kargs[] = {&a};
   const bool prof = prof_begin(ctx, s);
   UPB_CUDA(cudaLaunchCooperativeKernel((void*)k_sgnn<true>, dim3(grid), dim3(NT), kargs, SMEM_BYTES, s));
@@ -353,12 +369,6 @@ static_assert(sizeof(cudaIpcMemHandle_t) == UPB_PEER_HANDLE_BYTES, "IPC handle s
 extern "C" int upb_peer_export(upb_ctx* ctx, void* handle_out) {
   if (int rc = check_ctx(ctx, "peer_export")) return rc;
   if (!handle_out) return set_error(UPB_ERR_ARG, "peer_export: handle_out is null");
-  if (!ctx->xchg) {
-    const size_t bytes = sizeof(float) * 2 * G_ROW + sizeof(unsigned int) * 4 * MAX_PEERS;
-    UPB_CUDA(cudaMalloc(&ctx->xchg, bytes));
-    UPB_CUDA(cudaMemset(ctx->xchg, 0, bytes));
-    UPB_CUDA(cudaDeviceSynchronize());
-  }
   cudaIpcMemHandle_t h;
   UPB_CUDA(cudaIpcGetMemHandle(&h, ctx->xchg));
   memcpy(handle_out, &h, sizeof(h));
@@ -387,8 +397,13 @@ extern "C" int upb_peer_connect(upb_ctx* ctx, int world, int rank, const void* h
       return set_error(UPB_ERR_CUDA, buf);
     }
   }
-  UPB_CUDA(cudaMalloc(&ctx->peers_dev, sizeof(float*) * world));
+  // sequence numbers restart at 1 on every rank: forget the flags of earlier single-GPU steps.  The caller runs a
+  // collective after this call and before the first fused step (Engine.connect_peers), so no peer can push into this
+  // buffer before it is cleared.
+  UPB_CUDA(cudaDeviceSynchronize());
+  UPB_CUDA(cudaMemset(ctx->xchg + XCHG_FLAGS, 0, sizeof(float) * (XCHG_FLOATS - XCHG_FLAGS)));
   UPB_CUDA(cudaMemcpy(ctx->peers_dev, ptrs.data(), sizeof(float*) * world, cudaMemcpyHostToDevice));
+  UPB_CUDA(cudaDeviceSynchronize());
   ctx->peer_ptrs = ptrs;
   ctx->world = world;
   ctx->rank = rank;
@@ -396,11 +411,18 @@ extern "C" int upb_peer_connect(upb_ctx* ctx, int world, int rank, const void* h
   return UPB_OK;
 }
 
+extern "C" int upb_peer_timeouts(upb_ctx* ctx, int64_t* count) {
+  if (int rc = check_ctx(ctx, "peer_timeouts")) return rc;
+  if (!count) return set_error(UPB_ERR_ARG, "peer_timeouts: count is null");
+  unsigned int n = 0;
+  UPB_CUDA(cudaMemcpy(&n, ctx->gridbar + 6, sizeof(n), cudaMemcpyDeviceToHost));
+  *count = (int64_t)n;
+  return UPB_OK;
+}
+
 extern "C" int upb_next_step_fused(upb_ctx* ctx) {
   if (!ctx) return 0;
-  const bool clip_now = ctx->cfg.clip_mode == UPB_CLIP_ALWAYS ||
-                        (ctx->cfg.clip_mode == UPB_CLIP_REFERENCE && ctx->host_steps == 0);
-  return (!clip_now && ctx->coop) ? 1 : 0;
+  return (!clip_now(ctx) && ctx->coop) ? 1 : 0;
 }
 
 extern "C" int upb_read_losses(upb_ctx* ctx, const float* grad, float* out4_host, void* stream) {
@@ -451,7 +473,14 @@ extern "C" int upb_set_opt_state(upb_ctx* ctx, const float* m_host, const float*
   if (steps4_host) {
     UPB_CUDA(cudaMemcpy(ctx->steps + 4 * ctx->steps_cur, steps4_host, sizeof(long long) * 4, cudaMemcpyHostToDevice));
     ctx->host_steps = steps4_host[0];
+    ctx->clip_armed = steps4_host[0] == 0;
   }
+  return UPB_OK;
+}
+
+extern "C" int upb_rearm_clip(upb_ctx* ctx) {
+  if (int rc = check_ctx(ctx, "rearm_clip")) return rc;
+  ctx->clip_armed = true;
   return UPB_OK;
 }
 

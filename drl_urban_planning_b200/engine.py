@@ -187,6 +187,12 @@ class Engine:
         _lib.check(_lib.lib().upb_peer_connect(self._ctx, int(world), int(rank), C.c_char_p(handles)), "upb_peer_connect")
         self.peers = world
 
+    def peer_timeouts(self) -> int:
+        """CTAs that ever gave up waiting for a peer inside a fused step (sticky; non-zero = ranks out of sync)."""
+        n = C.c_int64()
+        _lib.check(_lib.lib().upb_peer_timeouts(self._ctx, C.byref(n)), "upb_peer_timeouts")
+        return int(n.value)
+
     def next_step_fused(self) -> bool:
         return bool(_lib.lib().upb_next_step_fused(self._ctx))
 
@@ -243,12 +249,15 @@ class Engine:
                    "upb_get_opt_state")
         return m, v, steps
 
-    def set_opt_state(self, m: np.ndarray, v: np.ndarray, steps: np.ndarray) -> None:
+    def set_opt_state(self, m: np.ndarray, v: np.ndarray, steps: np.ndarray, rearm_first_step_clip: bool = False
+                      ) -> None:
         m = np.ascontiguousarray(m, np.float32)
         v = np.ascontiguousarray(v, np.float32)
         steps = np.ascontiguousarray(steps, np.int64)
         _lib.check(_lib.lib().upb_set_opt_state(self._ctx, m.ctypes.data, v.ctypes.data, steps.ctypes.data),
                    "upb_set_opt_state")
+        if rearm_first_step_clip:
+            _lib.check(_lib.lib().upb_rearm_clip(self._ctx), "upb_rearm_clip")
 
     def profile(self, enable: bool) -> None:
         _lib.check(_lib.lib().upb_profile_enable(self._ctx, int(enable)), "upb_profile_enable")

@@ -34,14 +34,17 @@ except ImportError:                    # pragma: no cover
     _pyptr = None
 
 
-def _pointer_table(states: Sequence[Sequence]):
+def _pointer_table(states: Sequence[Sequence], n_cap: int, e_cap: int):
+    """Raw pointers of the 9 arrays of every state.  The packer reads n_cap / e_cap elements through them, so the
+    element counts are checked here (ValueError) -- a state padded to other widths would be an out-of-bounds read."""
     n = len(states)
     ptrs = np.empty(9 * n, dtype=np.uint64)
     keep = []
-    if _pyptr is not None and _pyptr.pointer_table(states, ptrs) < 0:
+    if _pyptr is not None and _pyptr.pointer_table(states, ptrs, int(n_cap), int(e_cap)) < 0:
         return ptrs, keep              # every array was already a C-contiguous buffer of the right item type
+    want = (52, n_cap * 23, e_cap * 2, 23, n_cap, e_cap, e_cap, n_cap, 3)
     k = 0
-    for st in states:
+    for i, st in enumerate(states):
         if len(st) != 9:
             raise ValueError("a state must hold 9 arrays (observation_extractor.py:207-228)")
         for j in range(9):
@@ -49,6 +52,9 @@ def _pointer_table(states: Sequence[Sequence]):
             if not (type(a) is np.ndarray and a.dtype == _DTYPES[j] and a.flags.c_contiguous):
                 a = _as_numpy(a, _DTYPES[j])
                 keep.append(a)
+            if (a.size < 2) if j == 8 else (a.size != want[j]):
+                raise ValueError(f"state {i}, array {j}: {a.size} elements, expected {want[j]} for the padded widths "
+                                 f"n_cap={n_cap}, e_cap={e_cap}")
             ptrs[k] = a.__array_interface__["data"][0]
             k += 1
     return ptrs, keep
@@ -119,7 +125,7 @@ def pack_states(states: Sequence[Sequence], n_cap: Optional[int] = None, e_cap: 
     if n_cap is None or e_cap is None:
         n_cap, e_cap = infer_caps(states)
     L = _lib.lib()
-    ptrs, keep = _pointer_table(states)
+    ptrs, keep = _pointer_table(states, n_cap, e_cap)
     if out_host is not None:
         # reuse the caller's (pinned) buffer: fill straight away, the blob header tells how many bytes were used;
         # only a too-small buffer costs the extra measuring pass below

@@ -11,9 +11,10 @@ scalars per minibatch -- but a different data path:
   * one encoder pass yields value, log-prob and entropy (the reference runs the encoder twice per step);
   * loss scalars stay on the device and are read back once per epoch (the reference syncs 4x per step).
 
-Data parallel: every rank holds the whole buffer and takes `perm[i*B:(i+1)*B][rank::world]` of each global minibatch;
-1/B and 1/|ind| are global, so the summed shard gradients equal the single-GPU batch gradient (SURVEY.md section
-8(e)).  The per-rank 58 KB column sums are exchanged inside the step kernel through peer memory (NVLink, no NCCL call,
+Data parallel: every rank holds the whole buffer and takes `order[i*B:(i+1)*B][rank::world]` of each global
+minibatch, where `order` is RANK 0's permutation broadcast once per epoch (the ranks' np.random streams need not
+agree) and `load_states` checks that all ranks hold the same buffer; 1/B and 1/|ind| are global, so the summed shard
+gradients equal the single-GPU batch gradient.  The per-rank 58 KB column sums are exchanged inside the step kernel through peer memory (NVLink, no NCCL call,
 one launch per step); steps that clip gradients, and process groups without peer access, all-reduce one 55 KB
 gradient+statistics buffer with NCCL instead.
 """
@@ -35,7 +36,7 @@ class PPOUpdater:
                  clip_epsilon: float = 0.2, value_pred_coef: float = 0.5, entropy_coef: float = 0.01,
                  gamma: float = 1.0, tau: float = 0.0, opt_num_epochs: int = 4, mini_batch_size: int = 256,
                  clip_mode: int = _lib.CLIP_REFERENCE, process_group="auto", pack_threads: int = 0,
-                 use_peers: bool = True):
+                 use_peers: bool = True, batch_stage: bool = False):
         self.device = torch.device(device)
         self.engine = Engine(self.device, n_cap, e_cap, lr=lr, eps=eps, clip_epsilon=clip_epsilon,
                              value_pred_coef=value_pred_coef, entropy_coef=entropy_coef, clip_mode=clip_mode)
@@ -49,14 +50,22 @@ class PPOUpdater:
         self.opt_num_epochs, self.mini_batch_size = opt_num_epochs, mini_batch_size
         self.value_pred_coef, self.entropy_coef = value_pred_coef, entropy_coef
         self.pack_threads = pack_threads
+        self.batch_stage = bool(batch_stage)            # agent_specs.batch_stage (urban_planning_agent.py:314-319)
         # process_group: "auto" = the default group if torch.distributed is initialised, None = single process,
         # or an explicit group
         self.world, self.rank = 1, 0
+        dist_up = torch.distributed.is_available() and torch.distributed.is_initialized()
         if process_group == "auto":
             process_group = None
-            use_dist = torch.distributed.is_available() and torch.distributed.is_initialized()
+            use_dist = dist_up
         else:
             use_dist = process_group is not None
+            if not use_dist and dist_up and torch.distributed.get_world_size() > 1:
+                import warnings
+                warnings.warn("PPOUpdater(process_group=None) runs single-process although torch.distributed is "
+                              "initialised with world_size > 1: every rank will update independently and the ranks "
+                              "diverge.  Pass process_group='auto' (or a group) for data-parallel updates.",
+                              RuntimeWarning, stacklevel=2)
         self.pg = process_group
         if use_dist:
             import torch.distributed as dist
@@ -87,7 +96,47 @@ class PPOUpdater:
         self.exps = torch.as_tensor(e).to(self.device)
         info = self.blob.info.astype(np.int64)
         self._cost = Engine.graph_cost(info)
+        self._stage = info[:, 3].copy()
+        self._check_same_buffer(info)
         return self.blob
+
+    def _check_same_buffer(self, info: np.ndarray) -> None:
+        """Data-parallel ranks must hold the SAME rollout buffer (the shards are index ranges into it)."""
+        if self.world <= 1:
+            return
+        import zlib
+        import torch.distributed as dist
+        sig = [int(info.shape[0]), zlib.crc32(np.ascontiguousarray(info).tobytes()),
+               zlib.crc32(np.ascontiguousarray(self.exps_host).tobytes()),
+               zlib.crc32(self.actions.cpu().numpy().tobytes())]
+        on = self.device if dist.get_backend(self.pg) == "nccl" else torch.device("cpu")
+        lo = torch.tensor(sig, dtype=torch.int64, device=on)
+        hi = lo.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=self.pg)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=self.pg)
+        if not torch.equal(lo, hi):
+            raise _lib.UpbError("data-parallel ranks hold different rollout buffers (count / graph sizes / exps / "
+                                "actions differ): every rank must load the same states")
+
+    def _epoch_order(self, order: np.ndarray) -> np.ndarray:
+        """Next epoch's sample order, composed like the reference: it re-permutes the ALREADY permuted lists every
+        epoch (urban_planning_agent.py:306-312 reassigns `states = index_select_list(states, perm_np)`), so epoch k
+        walks perm_1 o ... o perm_k; then the optional stage grouping (:314-319).  Every rank draws from np.random
+        (keeps the streams aligned when they are seeded alike) but rank 0's order is the one used."""
+        T = order.shape[0]
+        perm = np.arange(T)
+        np.random.shuffle(perm)                                                        # :306-307
+        order = order[perm]
+        if self.batch_stage:                                                           # get_perm_batch_stage :273-279
+            st = self._stage[order]
+            order = np.concatenate([order[st == 0], order[st != 0]])
+        if self.world > 1:
+            import torch.distributed as dist
+            on = self.device if dist.get_backend(self.pg) == "nccl" else torch.device("cpu")
+            t = torch.as_tensor(order.astype(np.int64), device=on)
+            dist.broadcast(t, src=dist.get_global_rank(self.pg, 0) if self.pg is not None else 0, group=self.pg)
+            order = t.cpu().numpy()
+        return order
 
     # ------------------------------------------------------------------ pieces of update_params
     def forward_all(self):
@@ -130,14 +179,19 @@ class PPOUpdater:
     def update_policy(self, iteration: int = 0, log_fn=None):
         T, B = self.blob.count, self.mini_batch_size
         nb = int(math.floor(T / B))
-        stats_all = torch.zeros(max(nb, 1), 8, dtype=torch.float32, device=self.device)
+        # one gradient / statistics row per minibatch of the epoch: the step kernels write their loss statistics
+        # straight into their own row (no per-step device copy), read back once per epoch
+        ring = getattr(self, "_grad_ring", None)
+        if ring is None or ring.shape[0] < max(nb, 1):
+            ring = torch.zeros(max(nb, 1), _lib.UPB_GRAD_STRIDE, dtype=torch.float32, device=self.device)
+            self._grad_ring = ring
         totals = np.zeros(4)
+        order = np.arange(T)
         for epoch in range(self.opt_num_epochs):
-            perm = np.arange(T)
-            np.random.shuffle(perm)                                                    # :306-307
+            order = self._epoch_order(order)
             # this rank's shard of every minibatch, ordered for the kernel's static CTA schedule (long + short graph
             # per CTA); one upload per epoch
-            shards = [self.engine.balance_ids(perm[i * B:(i + 1) * B][self.rank::self.world], self._cost)
+            shards = [self.engine.balance_ids(order[i * B:(i + 1) * B][self.rank::self.world], self._cost)
                       for i in range(nb)]
             width = max((len(x) for x in shards), default=0)
             ids_host = np.zeros((max(nb, 1), max(width, 1)), np.int32)
@@ -146,14 +200,19 @@ class PPOUpdater:
             ids_dev = torch.as_tensor(ids_host).to(self.device)
             for i in range(nb):
                 sl = slice(i * B, min((i + 1) * B, T))
-                n_ind = int((self.exps_host[perm[sl]] != 0).sum())
+                n_ind = int((self.exps_host[order[sl]] != 0).sum())
+                self.grad = ring[i]
                 self.minibatch_step(ids_dev[i, :len(shards[i])], sl.stop - sl.start, n_ind)
-                stats_all[i].copy_(self.grad[_lib.UPB_STAT_OFFSET:_lib.UPB_STAT_OFFSET + 8])
-            st = stats_all[:nb].cpu().numpy().astype(np.float64)                       # one sync per epoch
+            stats_all = ring[:nb, _lib.UPB_STAT_OFFSET:_lib.UPB_STAT_OFFSET + 16]
+            st = stats_all.cpu().numpy().astype(np.float64)                            # one sync per epoch
             nB, nI = np.maximum(st[:, 3], 1), np.maximum(st[:, 4], 1)
             vl, sl_, el = st[:, 0] / nB, st[:, 1] / nI, st[:, 2] / nI
             loss = sl_ + self.value_pred_coef * vl + self.entropy_coef * el
-            if st[:, 7].any():
+            if self.fused_exchange and self.engine.peer_timeouts():
+                raise _lib.UpbError("multi-GPU step: a peer rank never published its gradient sums (timed out inside "
+                                    "the step kernel); that step's Adam update was skipped on this rank -- the ranks "
+                                    "are out of sync, restore the last checkpoint")
+            if nb and st[:, 7].any():
                 raise FloatingPointError("non-finite value / log-prob / entropy in the PPO update")
             if log_fn is not None:
                 for i in range(nb):

@@ -150,7 +150,8 @@ int upb_ppo_step(upb_ctx* ctx, const void* blob_dev, const int32_t* ids, int cou
 /* ---- multi-GPU fused step (one process per GPU, peers on one node reachable over NVLink / NVSwitch or PCIe P2P) ----
  * The reference is single-process; data parallelism over the graphs of a minibatch is this library's extension
  * (SURVEY.md section 8e).  Without these calls the ranks exchange upb_ppo_grad's 55 KB buffer with ncclAllReduce and
- * call upb_apply.  With them the exchange happens inside upb_ppo_step's kernel through peer memory:
+ * call upb_apply.  With them the exchange happens inside upb_ppo_step's kernel through peer memory (every rank PUSHES
+ * its slice sums into all ranks' buffers with remote stores and flags each slice; nobody loads over NVLink):
  *   upb_peer_export   writes UPB_PEER_HANDLE_BYTES bytes (a CUDA IPC handle of this context's exchange buffer);
  *   upb_peer_connect  takes the `world` handles gathered from all ranks in rank order and maps the peers' buffers;
  *                     afterwards every rank must call upb_ppo_step the same number of times (empty shards included);
@@ -161,6 +162,11 @@ int upb_ppo_step(upb_ctx* ctx, const void* blob_dev, const int32_t* ids, int cou
 int upb_peer_export(upb_ctx* ctx, void* handle_out);
 int upb_peer_connect(upb_ctx* ctx, int world, int rank, const void* handles);
 int upb_next_step_fused(upb_ctx* ctx);
+/* Number of CTAs that, in any fused step of this context so far, gave up waiting for a peer rank's gradient sums
+ * (bounded polling instead of hanging the GPU).  Such a CTA SKIPS its Adam / parameter writes for that step, so no
+ * stale peer data is ever applied; the count is sticky.  Non-zero means the ranks are out of sync: stop and restore a
+ * checkpoint.  Synchronises the device (PPOUpdater checks it once per epoch). */
+int upb_peer_timeouts(upb_ctx* ctx, int64_t* count);
 
 /* the 4 scalars the reference logs per minibatch (urban_planning_agent.py:338-345), from a gradient buffer:
  * out4 = {loss, value_loss, surr_loss, entropy_loss}.  Synchronises `stream`. */
@@ -175,6 +181,11 @@ int upb_gae(upb_ctx* ctx, const float* rewards, const float* masks, const float*
  * pointers), steps int64[4] = {global step, encoder+value step, land-use-head step, road-head step}. */
 int upb_get_opt_state(upb_ctx* ctx, float* m_host, float* v_host, int64_t* steps4_host);
 int upb_set_opt_state(upb_ctx* ctx, const float* m_host, const float* v_host, const int64_t* steps4_host);
+/* UPB_CLIP_REFERENCE clips on the first optimiser step of a PROCESS (the parameters() generators of
+ * urban_planning_agent.py:46 are consumed by the first clip_grad_norm_ calls, agent_ppo.py:43-46).  A context starts
+ * armed; upb_set_opt_state with a non-zero global step disarms it ("continue as if never interrupted");
+ * upb_rearm_clip arms it again so that a run resumed from a checkpoint clips its first step like the reference does. */
+int upb_rearm_clip(upb_ctx* ctx);
 
 /* Kernel timing for the roofline line of bench.py: while enabled, upb_ppo_grad / upb_forward bracket the fused
  * SGNN kernel with CUDA events on the launching stream.  upb_profile_read synchronises the device and returns the

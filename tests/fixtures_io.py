@@ -39,3 +39,14 @@ def expand_states(z) -> List[list]:
                        z["stage"][i].copy()])
         no += n; eo += e
     return states
+
+
+def states_digest(states) -> str:
+    """sha256 over the compact form of the states (the big golden fixtures store this instead of the states, which
+    are regenerated from the seed by drl_urban_planning_b200/synth.py)."""
+    import hashlib
+    h = hashlib.sha256()
+    c = compact_states(states)
+    for k in sorted(c):
+        h.update(np.ascontiguousarray(c[k]).tobytes())
+    return h.hexdigest()

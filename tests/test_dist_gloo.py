@@ -90,3 +90,63 @@ def test_two_rank_shards_sum_to_batch_gradient():
     assert st[3] == B and st[4] == int((exps != 0).sum())
     assert np.isclose(st[0] / st[3], ref["value_loss"]) and np.isclose(st[1] / st[4], ref["surr_loss"])
     assert np.isclose(st[2] / st[4], ref["entropy_loss"])
+
+
+def _order_worker(rank, world, port, out):
+    """Host logic of PPOUpdater's sharding with DIFFERENT np.random seeds per rank (the usual torchrun setup)."""
+    import types
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from drl_urban_planning_b200.ppo import PPOUpdater
+    T = 37
+    info = np.stack([np.arange(T) + 5, np.arange(T) * 3, np.arange(T) % 7, np.arange(T) % 2], 1).astype(np.int32)
+    duck = types.SimpleNamespace(world=world, rank=rank, pg=None, device=torch.device("cpu"), batch_stage=False,
+                                 _stage=info[:, 3].astype(np.int64), exps_host=np.ones(T, np.float32),
+                                 actions=torch.zeros(T, 2))
+    PPOUpdater._check_same_buffer(duck, info.astype(np.int64))            # identical buffers: passes
+    np.random.seed(100 + rank)                                            # per-rank seeds
+    order = np.arange(T)
+    orders = []
+    for _ in range(3):
+        order = PPOUpdater._epoch_order(duck, order)
+        orders.append(order.copy())
+    bad = info.astype(np.int64).copy()
+    if rank == 1:
+        bad[3, 0] += 1                                                    # rank 1 holds a different buffer
+    try:
+        PPOUpdater._check_same_buffer(duck, bad)
+        mismatch_detected = False
+    except _lib.UpbError:
+        mismatch_detected = True
+    duck.batch_stage = True
+    staged = PPOUpdater._epoch_order(duck, np.arange(T))
+    out.put((rank, np.stack(orders), mismatch_detected, staged))
+    dist.destroy_process_group()
+
+
+def test_rank0_order_is_broadcast_and_buffers_are_checked():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_order_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs: p.start()
+    res = dict()
+    for _ in range(world):
+        r, orders, mismatch, staged = q.get(timeout=300)
+        res[r] = (orders, mismatch, staged)
+    for p in procs: p.join(timeout=60)
+    assert np.array_equal(res[0][0], res[1][0])                 # every rank walks rank 0's permutations
+    # rank 0's stream: composed permutations (urban_planning_agent.py:306-312)
+    np.random.seed(100)
+    order = np.arange(37)
+    for k in range(3):
+        perm = np.arange(37); np.random.shuffle(perm)
+        order = order[perm]
+        assert np.array_equal(res[0][0][k], order)
+        B = 8
+        for i in range(37 // B):                                # the two shards partition each global minibatch
+            mb = order[i * B:(i + 1) * B]
+            assert sorted(np.concatenate([mb[0::2], mb[1::2]]).tolist()) == sorted(mb.tolist())
+    assert res[0][1] and res[1][1]                              # both ranks see the mismatch
+    st = res[0][2] % 2                                          # stage = index % 2: land use first, road second
+    assert np.array_equal(res[0][2], res[1][2]) and (np.diff(st) >= 0).all()

@@ -100,6 +100,50 @@ def test_gradient_and_steps_match_reference_golden(name, golden_dir, dev):
         assert rel(params.cpu().numpy(), z["params_after"][k]) < 1e-5, k
 
 
+@pytest.mark.parametrize("name", ["hlg256", "dhm256", "grid64"])
+def test_baseline_size_minibatch_matches_reference_golden(name, golden_dir, dev):
+    """BASELINE.json sizes (HLG / DHM, 256 graphs per minibatch; the two-stage grid community) against vectors produced
+    by the unmodified reference: forward values, then three optimiser steps through upb_ppo_step exactly as the product
+    runs them (ids in the LPT order of Engine.balance_ids, full grid of CTAs, fused tail from step 2 on; step 1 clips
+    and takes the two-call path like the reference's first step): losses, all 32 gradients and the parameter
+    trajectory."""
+    from drl_urban_planning_b200.engine import Engine
+    from fixtures_io import states_digest
+    z = np.load(os.path.join(golden_dir, name + ".npz"))
+    states, actions = synth.make_states(int(z["seed"]), str(z["community"]), int(z["count"]))
+    assert states_digest(states) == str(z["digest"]), "synth.py no longer reproduces the fixture's states"
+    assert np.array_equal(actions, z["actions"])
+    B = len(states)
+    blob = pack_states(states).to(dev)
+    eng = make_engine(dev, blob.n_cap, blob.e_cap, clip_mode=_lib.CLIP_REFERENCE)
+    params = t(z["params"], dev).clone()
+    value, logp, ent, greedy = eng.forward(blob, params, t(z["actions"], dev), want_greedy=True)
+    assert rel(value.cpu().numpy(), z["values"].ravel()) < TOL
+    assert rel(logp.cpu().numpy(), z["log_probs"].ravel()) < TOL
+    assert rel(ent.cpu().numpy(), z["entropies"].ravel()) < TOL
+    stage = np.array([int(s[8][:2].argmax()) for s in states])
+    assert np.array_equal(greedy.cpu().numpy().astype(np.int64), z["greedy"][np.arange(B), stage].astype(np.int64))
+    n_ind = int((z["exps"] != 0).sum())
+    args = (t(z["actions"], dev), t(z["advantages"], dev), t(z["returns"], dev), t(z["fixed_log_probs"], dev),
+            t(z["exps"], dev))
+    ids = eng.balance_ids(np.arange(B), Engine.graph_cost(blob.info.astype(np.int64)))
+    ids_dev = t(ids.astype(np.int32), dev)
+    launches = []
+    for k in range(3):
+        before = eng.launches
+        grad = eng.ppo_step(blob, params, *args, 1.0 / B, 1.0 / n_ind, ids=ids_dev)
+        launches.append(eng.launches - before)
+        losses = eng.read_losses(grad)
+        g = grad.cpu().numpy()
+        assert np.allclose(losses, z["losses"][k], rtol=1e-4, atol=1e-5), (k, losses, z["losses"][k])
+        worst, where = per_tensor_rel(g[:PL.NUM_PARAMS], z["grads"][k])
+        assert worst < TOL, (k, worst, where)
+        st = g[_lib.UPB_STAT_OFFSET:_lib.UPB_STAT_OFFSET + 8]
+        assert st[3] == B and st[4] == n_ind and st[7] == 0
+        assert rel(params.cpu().numpy(), z["params_after"][k]) < 1e-5, k
+    assert launches == [3, 1, 1]       # clipping step: kernel + reduce + apply; then one cooperative launch per step
+
+
 @pytest.mark.parametrize("community,count,seed", [("tiny", 64, 1), ("small", 48, 2), ("grid", 12, 3), ("dhm", 6, 4)])
 def test_matches_numpy_oracle(community, count, seed, dev):
     states, actions = synth.make_states(seed, community, count)

@@ -119,3 +119,54 @@ def test_gae_known_answer():
     a, R = ON.estimate_advantages(r, m, v, 1.0, 0.0)
     assert np.allclose(a.ravel(), [1 + 0.25 - 0.5, 2 - 0.25, 3 + 2 + 1, 4 - 2])
     assert np.allclose(R.ravel(), [1.25, 2.0, 5.0, 4.0])
+
+
+@pytest.mark.parametrize("name", ["hlg256", "dhm256", "grid64"])
+def test_numpy_oracle_matches_reference_at_baseline_sizes(name, golden_dir):
+    """BASELINE.json sizes: the f64 oracle against the reference-generated vectors of a 256-graph HLG / DHM minibatch
+    and the two-stage grid community (states regenerated from the seed; the digest guards the generator)."""
+    from drl_urban_planning_b200 import synth
+    from fixtures_io import states_digest
+    z = np.load(os.path.join(golden_dir, name + ".npz"))
+    states, actions = synth.make_states(int(z["seed"]), str(z["community"]), int(z["count"]))
+    assert states_digest(states) == str(z["digest"])
+    r = ON.ppo_minibatch(z["params"], states, z["actions"], z["advantages"], z["returns"],
+                         z["fixed_log_probs"], z["exps"])
+    assert rel(r["value"], z["values"].reshape(-1)) < 2e-5
+    assert rel(r["log_prob"], z["log_probs"].reshape(-1)) < 2e-5
+    assert rel(r["entropy"], z["entropies"].reshape(-1)) < 2e-5
+    got = [r["loss"], r["value_loss"], r["surr_loss"], r["entropy_loss"]]
+    assert np.allclose(got, z["losses"][0], rtol=2e-5, atol=2e-6)
+    assert per_tensor_rel(r["grad"], z["grads"][0]) < 1e-4
+
+
+def test_torch_port_update_policy_matches_reference(golden_dir):
+    """The multi-epoch trajectory of the unmodified reference's update_params / update_policy (composed epoch
+    permutations, urban_planning_agent.py:306-312) reproduced by the oracle port driven the same way."""
+    import math
+    z = np.load(os.path.join(golden_dir, "update_small.npz"))
+    T, B, epochs, np_seed = (int(x) for x in z["cfg"])
+    states = expand_states(z)
+    agent = TP.PortAgent(z["params"])
+    b_all = TP.stack_states(states)
+    act = torch.tensor(z["actions"])
+    with torch.no_grad():
+        values = TP.value(agent.params(), b_all)
+    adv, ret = TP.estimate_advantages(torch.tensor(z["rewards"]), torch.tensor(z["masks"]), values,
+                                      float(z["gamma_tau"][0]), float(z["gamma_tau"][1]))
+    with torch.no_grad():
+        fixed, _ = TP.log_prob_entropy(agent.params(), b_all, act)
+    exps_t = torch.tensor(z["exps"])
+    np.random.seed(np_seed)
+    order, losses = np.arange(T), []
+    for _ in range(epochs):
+        perm = np.arange(T)
+        np.random.shuffle(perm)
+        order = order[perm]
+        for i in range(int(math.floor(T / B))):
+            idx = order[i * B:(i + 1) * B]
+            b = TP.stack_states([states[j] for j in idx])
+            ind = exps_t[idx].nonzero(as_tuple=False).squeeze(1)
+            losses.append(agent.step(b, act[idx], adv[idx], ret[idx], fixed[idx], ind))
+    assert np.allclose(np.array(losses), z["losses"], rtol=2e-5, atol=2e-6)
+    assert rel(agent.flat(), z["params_after"]) < 5e-6
