@@ -224,6 +224,35 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
+// ---- bulk asynchronous copies (TMA, 1-D): one elected thread issues cp.async.bulk global -> shared for a whole blob
+// section; completion is counted in bytes on an mbarrier that every thread then waits on (UBLKCP / SYNCS in SASS).
+// Sources and destinations are 16-byte aligned and sizes multiples of 16 (blob sections are padded for this).
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+// generic-proxy accesses (ordinary loads / stores) before this fence are ordered before later async-proxy (bulk copy)
+// accesses to the same memory
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, unsigned bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}"
+      ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 __device__ __forceinline__ float4 f4(float a) { return make_float4(a, a, a, a); }
@@ -1165,7 +1194,7 @@ __device__ __forceinline__ void softmax_seeds(const StepArgs& a, const BlobHeade
 
 template <bool TRAIN, bool BIG>
 __device__ void graph_body(const StepArgs& a, const BlobHeader& hd, const GraphDesc& d, int gid, float* smem,
-                           float* gp, float* scr, bool first_item) {
+                           float* gp, float* scr, bool first_item, uint64_t* mbar, unsigned mpar) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int q = tid & 3;
   UPB_STAMP(0);
@@ -1209,27 +1238,21 @@ __device__ void graph_body(const StepArgs& a, const BlobHeader& hd, const GraphD
     uint32_t* adj_s = reinterpret_cast<uint32_t*>(smem + S_ADJ);
     uint32_t* cuv_s = reinterpret_cast<uint32_t*>(smem + S_CUV);
     int* cidx_s = reinterpret_cast<int*>(smem + S_CIDX);
-    // stage the graph's neighbourhood lists and node features in shared memory (asynchronous 16-byte copies; blob
-    // sections are padded).  The features park in the EPQ region, which is idle until the first EPQ phase.
-    {
-      const uint4* s0 = reinterpret_cast<const uint4*>(rp_g);
-      uint4* d0 = reinterpret_cast<uint4*>(rp_s);
-      for (int i = tid; i < (n + 1 + 7) / 8; i += NT) cp_async16(d0 + i, s0 + i);
-      const uint4* so = reinterpret_cast<const uint4*>(ord_g);
-      uint4* dord = reinterpret_cast<uint4*>(smem + S_ORD);
-      for (int i = tid; i < d.ord_rounds * NW; i += NT) cp_async16(dord + i, so + i);   // 8 node ids per warp-task
-      const uint4* s1 = reinterpret_cast<const uint4*>(adj_g);
-      uint4* d1 = reinterpret_cast<uint4*>(adj_s);
-      for (int i = tid; i < (2 * e + 3) / 4; i += NT) cp_async16(d1 + i, s1 + i);
-      const uint4* s2 = reinterpret_cast<const uint4*>(cuv_g);
-      const uint4* s3 = reinterpret_cast<const uint4*>(cidx_g);
-      uint4* d2 = reinterpret_cast<uint4*>(cuv_s);
-      uint4* d3 = reinterpret_cast<uint4*>(cidx_s);
-      for (int i = tid; i < (k + 3) / 4; i += NT) { cp_async16(d2 + i, s2 + i); cp_async16(d3 + i, s3 + i); }
-      const float4* sx = reinterpret_cast<const float4*>(g.x);
-      float4* dx = reinterpret_cast<float4*>(smem + S_EPQ);
-      for (int i = tid; i < n * 6; i += NT) cp_async16(dx + i, sx + i);
-      cp_async_commit();
+    // stage the graph's neighbourhood lists and node features in shared memory: one bulk copy (TMA) per blob section,
+    // issued by one thread, all in flight together; blob sections are padded to 16 bytes.  The features park in the EPQ
+    // region, which is idle until the first EPQ phase.  (reference op being staged: the per-sample gathers of
+    // state_encoder.py:110-148 read these neighbourhoods from padded (B, E, .) tensors)
+    if (tid == 0) {
+      const unsigned b_rp = (unsigned)((n + 1 + 7) / 8) * 16u, b_ord = (unsigned)(d.ord_rounds * NW) * 16u;
+      const unsigned b_adj = (unsigned)((2 * e + 3) / 4) * 16u, b_k = (unsigned)((k + 3) / 4) * 16u;
+      const unsigned b_x = (unsigned)n * (FS * 4u);
+      fence_proxy_async();                     // the previous graph's ordinary accesses to these regions come first
+      mbar_expect_tx(mbar, b_rp + b_ord + b_adj + 2u * b_k + b_x);
+      bulk_g2s(rp_s, rp_g, b_rp, mbar);
+      if (b_ord) bulk_g2s(smem + S_ORD, ord_g, b_ord, mbar);
+      if (b_adj) bulk_g2s(adj_s, adj_g, b_adj, mbar);
+      if (b_k) { bulk_g2s(cuv_s, cuv_g, b_k, mbar); bulk_g2s(cidx_s, cidx_g, b_k, mbar); }
+      bulk_g2s(smem + S_EPQ, g.x, b_x, mbar);
     }
     g.rp = rp_s; g.adj = adj_s; g.cuv = cuv_s; g.cidx = cidx_s;
     g.ord = reinterpret_cast<const uint16_t*>(smem + S_ORD);
@@ -1247,7 +1270,7 @@ __device__ void graph_body(const StepArgs& a, const BlobHeader& hd, const GraphD
     if (tid == 113) sc[SC_ADV] = a.adv[gid];
   }
   if (tid == 114) reinterpret_cast<int*>(sc)[SC_QUEUE] = 0;
-  if constexpr (!BIG) cp_async_wait_all();
+  if constexpr (!BIG) mbar_wait(mbar, mpar);
   __syncthreads();
   UPB_STAMP(1);
 
@@ -1593,6 +1616,7 @@ __device__ void graph_body(const StepArgs& a, const BlobHeader& hd, const GraphD
     float t = sV[V_GHC + c];
 #pragma unroll
     for (int r = 0; r < 16; ++r) t = fmaf(sW[S_QC + r * 16 + c], __shfl_sync(0xffffffffu, gqp, r), t);
+    __syncwarp();                                  // lanes c and c + 16 both read V_GHC[c] above (racecheck)
     if (lane < 16) { sV[V_GHC + c] = t; sV[V_GQP + c] = gqp; }
   }
   if (g.stage == 1) {   // road head feeds h^L of its candidate nodes directly
@@ -1626,10 +1650,13 @@ __device__ void graph_body(const StepArgs& a, const BlobHeader& hd, const GraphD
       if constexpr (BIG) {
 #pragma unroll 2
         for (int i = tid; i < n * 8; i += NT) st4(g.EPQ + i * 4, __ldcg(reinterpret_cast<const float4*>(E0g) + i));
-      } else {   // same thread wrote the same elements in the forward pass
-        for (int i = tid; i < n * 8; i += NT) cp_async16(g.EPQ + i * 4, E0g + i * 4);
-        cp_async_commit();
-        cp_async_wait_all();
+      } else {   // one bulk copy; the forward pass's __stcg stores to E0g were ordered by the barriers since
+        if (tid == 0) {
+          fence_proxy_async();
+          mbar_expect_tx(mbar + 1, (unsigned)n * 128u);
+          bulk_g2s(g.EPQ, E0g, (unsigned)n * 128u, mbar + 1);
+        }
+        mbar_wait(mbar + 1, mpar);
       }
       exact = exact_first;
       __syncthreads();
@@ -1694,16 +1721,17 @@ __device__ void graph_body(const StepArgs& a, const BlobHeader& hd, const GraphD
   {
     float* redbuf = smem + S_GPQ;                // [NW][384]  (GPQ is dead after the last g_h)
     const float* xsrc = g.x;
-    if constexpr (!BIG) {                        // features back into the (dead) EPQ region, one asynchronous sweep
-      const float4* sx = reinterpret_cast<const float4*>(g.x);
-      float4* dx = reinterpret_cast<float4*>(smem + S_EPQ);
-      for (int i = tid; i < n * 6; i += NT) cp_async16(dx + i, sx + i);
-      cp_async_commit();
+    if constexpr (!BIG) {                        // features back into the (dead) EPQ region, one bulk copy
+      if (tid == 0) {
+        fence_proxy_async();
+        mbar_expect_tx(mbar + 2, (unsigned)n * (FS * 4u));
+        bulk_g2s(smem + S_EPQ, g.x, (unsigned)n * (FS * 4u), mbar + 2);
+      }
       xsrc = smem + S_EPQ;
     }
     float4 hs = f4(0.f);
     for (int task = tid; task < n * 4; task += NT) hs = hs + ld4(g.H + (task >> 2) * 16 + q * 4);
-    if constexpr (!BIG) { cp_async_wait_all(); __syncthreads(); }
+    if constexpr (!BIG) { mbar_wait(mbar + 2, mpar); __syncthreads(); }
     const int tcc = lane / 6, tf = lane % 6;     // 4 channel tiles x 6 feature tiles (lanes 24..31 idle)
     float acc[4][4];
 #pragma unroll
@@ -2072,7 +2100,13 @@ __device__ void fused_tail(const StepArgs& a, float* smem, unsigned stage_bits) 
 template <bool TRAIN>
 __global__ void __launch_bounds__(NT, 1) k_sgnn(const __grid_constant__ StepArgs a) {
   extern __shared__ __align__(16) float smem[];
+  __shared__ __align__(8) uint64_t s_mbar[3];   // bulk-copy completion: [0] graph staging, [1] EPQ reload, [2] feature reload
   const long long t_cta0 = a.stamps ? clock64() : 0;
+  if (threadIdx.x == 0) {
+    mbar_init(s_mbar + 0, 1); mbar_init(s_mbar + 1, 1); mbar_init(s_mbar + 2, 1);
+    fence_mbar_init();
+  }
+  unsigned nstaged = 0;                         // graphs staged by bulk copies so far: phase parity of the mbarriers
   load_weights(a.params, smem);
   float* gp = nullptr;
   if constexpr (TRAIN) {
@@ -2114,8 +2148,9 @@ __global__ void __launch_bounds__(NT, 1) k_sgnn(const __grid_constant__ StepArgs
       }
     }
     const bool big = d.n > NS || 2 * d.e > AS || d.k > KS || d.ord_rounds > ORD_ROUNDS;
-    if (big) graph_body<TRAIN, true>(a, hd, d, gid, smem, gp, scr, item == (int)(blockIdx.x + gridDim.x));   // stamps: the SECOND graph of CTA 0 (steady state)
-    else graph_body<TRAIN, false>(a, hd, d, gid, smem, gp, scr, item == (int)(blockIdx.x + gridDim.x));   // stamps: the SECOND graph of CTA 0 (steady state)
+    // stamps: the SECOND graph of CTA 0 (steady state)
+    if (big) graph_body<TRAIN, true>(a, hd, d, gid, smem, gp, scr, item == (int)(blockIdx.x + gridDim.x), s_mbar, 0u);
+    else { graph_body<TRAIN, false>(a, hd, d, gid, smem, gp, scr, item == (int)(blockIdx.x + gridDim.x), s_mbar, nstaged & 1u); ++nstaged; }
     __syncthreads();
   }
   if (a.stamps && threadIdx.x == 0 && blockIdx.x < 160) a.stamps[64 + blockIdx.x] = clock64() - t_cta0;           // CTA busy time

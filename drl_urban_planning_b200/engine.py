@@ -292,6 +292,13 @@ class Engine:
             return ids[np.argsort(-np.asarray(cost)[ids], kind="stable")]
         c = np.asarray(cost, dtype=np.float64)[ids]
         order = np.argsort(-c, kind="stable")
+        m = len(ids)
+        if m <= 2 * g and c[order[0]] < c[order[g - 1]] + c[order[-1]]:
+            # closed form of the loop below for one partial second round (the usual 256 graphs on 148 CTAs): no single
+            # graph outweighs a pair, so LPT pairs the (g - j)-th largest with the (g + j)-th largest; pairs first
+            srt = ids[order]
+            npair = m - g
+            return np.concatenate([srt[g - npair:g], srt[:g - npair], srt[m - 1:g - 1:-1] if npair else srt[:0]])
         bins = [[] for _ in range(g)]
         heap = [(0.0, b) for b in range(g)]
         for k in order:

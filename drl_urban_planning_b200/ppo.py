@@ -86,8 +86,15 @@ class PPOUpdater:
     # ------------------------------------------------------------------ buffer
     def load_states(self, states: Sequence, actions, exps=None):
         """Pack + upload the iteration's rollout states (list of reference 9-array states) and their actions."""
-        self.blob = pack_states(states, self.engine.n_cap, self.engine.e_cap, threads=self.pack_threads)
+        nvtx = torch.cuda.nvtx
+        nvtx.range_push("upb.pack_states")
+        self.blob = pack_states(states, self.engine.n_cap, self.engine.e_cap, threads=self.pack_threads,
+                                out_host=getattr(self, "_host_blob_buf", None))
+        self._host_blob_buf = self.blob.host if hasattr(self.blob.host, "data_ptr") else None
+        nvtx.range_pop()
+        nvtx.range_push("upb.upload_blob")
         self.blob.to(self.device, out=self._dev_blob_buf)
+        nvtx.range_pop()
         self._dev_blob_buf = self.blob.dev
         T = self.blob.count
         self.actions = torch.as_tensor(np.ascontiguousarray(actions, np.float32)).reshape(T, 2).to(self.device)
@@ -186,23 +193,31 @@ class PPOUpdater:
             ring = torch.zeros(max(nb, 1), _lib.UPB_GRAD_STRIDE, dtype=torch.float32, device=self.device)
             self._grad_ring = ring
         totals = np.zeros(4)
-        order = np.arange(T)
-        for epoch in range(self.opt_num_epochs):
+
+        def prepare(order):
+            """Host side of one epoch: the sample order, this rank's shard of every minibatch in the order of the
+            kernel's static CTA schedule (long + short graph per CTA), one upload."""
             order = self._epoch_order(order)
-            # this rank's shard of every minibatch, ordered for the kernel's static CTA schedule (long + short graph
-            # per CTA); one upload per epoch
             shards = [self.engine.balance_ids(order[i * B:(i + 1) * B][self.rank::self.world], self._cost)
                       for i in range(nb)]
             width = max((len(x) for x in shards), default=0)
             ids_host = np.zeros((max(nb, 1), max(width, 1)), np.int32)
             for i, x in enumerate(shards):
                 ids_host[i, :len(x)] = x
-            ids_dev = torch.as_tensor(ids_host).to(self.device)
+            n_ind = [int((self.exps_host[order[i * B:(i + 1) * B]] != 0).sum()) for i in range(nb)]
+            return order, [len(x) for x in shards], torch.as_tensor(ids_host).to(self.device, non_blocking=True), n_ind
+
+        cur = prepare(np.arange(T))
+        for epoch in range(self.opt_num_epochs):
+            torch.cuda.nvtx.range_push(f"upb.epoch{epoch}")
+            order, lens, ids_dev, n_inds = cur
             for i in range(nb):
-                sl = slice(i * B, min((i + 1) * B, T))
-                n_ind = int((self.exps_host[order[sl]] != 0).sum())
                 self.grad = ring[i]
-                self.minibatch_step(ids_dev[i, :len(shards[i])], sl.stop - sl.start, n_ind)
+                self.minibatch_step(ids_dev[i, :lens[i]], min((i + 1) * B, T) - i * B, n_inds[i])
+            # the next epoch's host work overlaps this epoch's kernels (one process; with several ranks the order is
+            # broadcast on the stream, which would wait for them)
+            if epoch + 1 < self.opt_num_epochs and self.world == 1:
+                cur = prepare(order)
             stats_all = ring[:nb, _lib.UPB_STAT_OFFSET:_lib.UPB_STAT_OFFSET + 16]
             st = stats_all.cpu().numpy().astype(np.float64)                            # one sync per epoch
             nB, nI = np.maximum(st[:, 3], 1), np.maximum(st[:, 4], 1)
@@ -227,6 +242,9 @@ class PPOUpdater:
                 log_fn("loss/epoch_entropy_loss", float(el.sum()), ge)
             self.loss_iter += nb
             totals += [loss.sum(), vl.sum(), sl_.sum(), el.sum()]
+            torch.cuda.nvtx.range_pop()
+            if epoch + 1 < self.opt_num_epochs and self.world > 1:
+                cur = prepare(order)
         totals /= max(self.opt_num_epochs, 1)
         if log_fn is not None:
             log_fn("loss/total_loss", float(totals[0]), iteration)

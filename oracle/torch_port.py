@@ -202,9 +202,9 @@ class PortAgent:
     """
 
     def __init__(self, flat_init: np.ndarray, lr=4e-4, eps=1e-5, clip_epsilon=0.2, value_pred_coef=0.5,
-                 entropy_coef=0.01, reference_clip=True):
+                 entropy_coef=0.01, reference_clip=True, device="cpu"):
         flat_init = np.asarray(flat_init, dtype=np.float32)
-        self.P = {s.name: torch.tensor(flat_init[s.offset:s.offset + s.size].reshape(s.shape).copy(),
+        self.P = {s.name: torch.tensor(flat_init[s.offset:s.offset + s.size].reshape(s.shape).copy(), device=device,
                                        requires_grad=True) for s in PL.SLOTS.values()}
         self.opt = torch.optim.Adam(list(self.P.values()), lr=lr, eps=eps, weight_decay=0.0)
         self.clip_epsilon, self.value_pred_coef, self.entropy_coef = clip_epsilon, value_pred_coef, entropy_coef

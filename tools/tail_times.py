@@ -21,7 +21,7 @@ for _ in range(4): eng.ppo_step(*args, ids=ids)
 stamps = torch.zeros(384, dtype=torch.int64, device=dev)
 eng.set_stamp_buffer(stamps); eng.ppo_step(*args, ids=ids); torch.cuda.synchronize()
 st = stamps.cpu().numpy()
-print("CTA0: wait at barrier 1 %d | stage counts + column reduce + Adam %d | wait at barrier 2 %d | chain + Adam(attention) %d cycles"
-      % (st[41] - st[40], st[42] - st[41], st[43] - st[42], st[44] - st[43]))
+print("CTA0: wait at the grid barrier %d | slice sums + push + flags %d | flag wait + reduce + Adam %d cycles"
+      % (st[41] - st[40], st[42] - st[41], st[43] - st[42]))
 busy = st[64:64 + eng.grid]
 print("busy (graphs only) max %d mean %.0f" % (busy.max(), busy.mean()))
