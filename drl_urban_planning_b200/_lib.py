@@ -14,6 +14,10 @@ UPB_GRAD_STRIDE = 13760
 UPB_STAT_OFFSET = 13732
 UPB_STAT_COUNT = 28
 
+UPB_MLP_NUM_PARAMS = 10257           # rl-mlp ablation model (include/upb200.h)
+UPB_MLP_GRAD_STRIDE = 10288
+UPB_MLP_STAT_OFFSET = 10260
+
 CLIP_REFERENCE, CLIP_ALWAYS, CLIP_NEVER = 0, 1, 2
 
 
@@ -61,6 +65,14 @@ _PROTOS = {
     "upb_set_stamp_buffer": (C.c_int, [_VP, _VP]),
     "upb_launch_count": (C.c_int64, [_VP]),
     "upb_select_action": (C.c_int, [_VP, _VP, _VP, C.c_int, _VP, _VP, _VP, _VP]),
+    "upb_mlp_forward": (C.c_int, [_VP, _VP, _VP, C.c_int, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "upb_mlp_select_action": (C.c_int, [_VP, _VP, _VP, C.c_int, _VP, _VP, _VP, _VP]),
+    "upb_mlp_ppo_grad": (C.c_int, [_VP, _VP, _VP, C.c_int, _VP, _VP, _VP, _VP, _VP, _VP, C.c_float, C.c_float,
+                                   _VP, _VP]),
+    "upb_mlp_apply": (C.c_int, [_VP, _VP, _VP, _VP]),
+    "upb_mlp_read_losses": (C.c_int, [_VP, _VP, C.POINTER(C.c_float), _VP]),
+    "upb_mlp_get_opt_state": (C.c_int, [_VP, _VP, _VP, _VP]),
+    "upb_mlp_set_opt_state": (C.c_int, [_VP, _VP, _VP, _VP]),
     "upb_peer_export": (C.c_int, [_VP, _VP]),
     "upb_peer_connect": (C.c_int, [_VP, C.c_int, C.c_int, _VP]),
     "upb_next_step_fused": (C.c_int, [_VP]),

@@ -57,28 +57,34 @@ class B200Update:
             raise _lib.UpbError("use_b200_update needs agent.device to be a CUDA device (train.py --use_nvidia_gpu)")
         # everything the kernels are specialised for is checked BEFORE a CUDA context / updater is built
         # (heads = 2 or another layer count has the same flat shapes but different maths)
-        from .model import _check_specs
-        _check_specs(cfg)
+        kind = getattr(cfg, "agent", "rl-sgnn")
+        if kind == "rl-sgnn":
+            from .model import _check_specs
+            _check_specs(cfg)
+            self.layout, model = PL.SGNN, "sgnn"
+        elif kind == "rl-mlp":                     # the ablation agent of train.py:18 (models/model.py:22-33)
+            from .mlp import _check_mlp_specs
+            _check_mlp_specs(cfg)
+            self.layout, model = PL.MLP, "mlp"
+        else:
+            raise NotImplementedError(f"agent '{kind}' has no learned update (rule / GA baselines)")
         if getattr(cfg, "weightdecay", 0.0) != 0.0:
             raise NotImplementedError("weight decay != 0 is not used by any shipped cfg")
-        if getattr(cfg, "agent", "rl-sgnn") != "rl-sgnn":
-            raise NotImplementedError("use_b200_update drives the rl-sgnn agent; the rl-mlp ablation has its own "
-                                      "entry points (drl_urban_planning_b200.mlp)")
         se = cfg.state_encoder_specs
         self.updater = PPOUpdater(
-            PL.from_state_dict(agent.actor_critic_net.state_dict()), se["max_num_nodes"], se["max_num_edges"], dev,
+            self.layout.from_state_dict(agent.actor_critic_net.state_dict()), se["max_num_nodes"], se["max_num_edges"], dev,
             lr=cfg.lr, eps=cfg.eps, clip_epsilon=cfg.clip_epsilon, value_pred_coef=cfg.value_pred_coef,
             entropy_coef=cfg.entropy_coef, gamma=cfg.gamma, tau=cfg.tau, opt_num_epochs=cfg.num_optim_epoch,
             mini_batch_size=cfg.mini_batch_size, clip_mode=clip_mode, process_group=process_group,
-            batch_stage=bool(cfg.agent_specs.get("batch_stage", False)))
+            batch_stage=bool(cfg.agent_specs.get("batch_stage", False)), model=model)
 
     def push_weights(self):
         """agent modules -> updater (e.g. after load_checkpoint / freeze_*)."""
-        flat = PL.from_state_dict(self.agent.actor_critic_net.state_dict())
+        flat = self.layout.from_state_dict(self.agent.actor_critic_net.state_dict())
         self.updater.params.copy_(torch.as_tensor(flat, device=self.updater.params.device))
 
     def pull_weights(self):
-        sd = PL.to_state_dict(self.updater.flat_params())
+        sd = self.layout.to_state_dict(self.updater.flat_params())
         ref = self.agent.actor_critic_net.state_dict()
         self.agent.actor_critic_net.load_state_dict({k: torch.as_tensor(v).to(ref[k].device) for k, v in sd.items()})
 

@@ -12,8 +12,10 @@
 //   uint16     rowptr[...]           per graph n+1 entries (CSR over the symmetrised adjacency), padded to 8
 //   uint16     order[...]            per graph the pull schedule: rounds x 16 warps x 8 node ids (0xFFFF = none),
 //                                    8-node groups of similar degree, assigned to the 16 warps longest-first (LPT)
-//   uint32     adj[...]              per graph 2e directed entries: neighbour | (slot+1) << 16, padded to 4
-//                                    slot = rank of the entry's undirected edge among the land-use candidates
+//   uint32     adj[...]              per graph 2e directed entries: neighbour | (slot+1) << 16 | first << 31, padded to 4
+//                                    slot = rank of the entry's undirected edge among the land-use candidates (15 bits);
+//                                    first = 1 when the row's node is the edge's first endpoint (edge_index[j][0]): the
+//                                    rl-mlp encoder picks an endpoint by position (state_encoder.py:269-276)
 //   uint32     cand_uv[...]          per graph k candidates of the active stage: u | v << 16 (edges) or node id
 //   int32      cand_idx[...]         original edge / node index of each candidate (action ids), padded to 4
 #pragma once
@@ -27,6 +29,8 @@ constexpr int kNumDim = 52;
 constexpr int kPullWarps = 16;      // warps of the fused kernel (NT / 32); the pull schedule is laid out for them
 constexpr int kPullGroup = 8;       // nodes per warp-task (4 lanes per node)
 constexpr uint16_t kNoNode = 0xFFFFu;
+constexpr uint32_t kAdjFirst = 0x80000000u;   // adj entry: the row's node is the first endpoint of the edge
+constexpr uint32_t kAdjSlotMask = 0x7FFFu;    // (entry >> 16) & kAdjSlotMask = candidate slot + 1
 
 struct BlobHeader {
   uint32_t magic;

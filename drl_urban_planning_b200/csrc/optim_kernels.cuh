@@ -103,6 +103,8 @@ struct ApplyArgs {
   long long* steps_out;       // [4] written by block 0 (ping-pong with steps_in across calls)
   float lr, beta1, beta2, eps;
   int clip_now;               // 1: two-group clip on this step (decided on the host: mode + first-step latch)
+  // flat layout of the model being updated (SGNN: layout.h; rl-mlp: mlp_kernel.cuh)
+  int num_params, encoder_end, policy_end, lu_begin, rd_begin, stat_offset;
 };
 
 constexpr int AP_THREADS = 512;
@@ -128,17 +130,17 @@ __global__ void __launch_bounds__(AP_THREADS) k_apply(const ApplyArgs a) {
   __shared__ float red[AP_THREADS / 32];
   __shared__ float sh[8];
   const int t = threadIdx.x;
-  const float* st = a.grad + UPB_STAT_OFFSET;
+  const float* st = a.grad + a.stat_offset;
   const bool live_lu = st[5] > 0.f, live_rd = st[6] > 0.f;
   const long long gstep = a.steps_in[0];
   const bool do_clip = a.clip_now != 0;
   float c_enc = 1.f, c_pol = 1.f, c_val = 1.f;
   if (do_clip) {
     float se = 0.f, sp = 0.f, sv = 0.f;
-    for (int i = t; i < NUM_PARAMS; i += AP_THREADS) {
+    for (int i = t; i < a.num_params; i += AP_THREADS) {
       const float g = a.grad[i];
-      if (i < ENCODER_END) se += g * g;
-      else if (i < POLICY_END) sp += g * g;
+      if (i < a.encoder_end) se += g * g;
+      else if (i < a.policy_end) sp += g * g;
       else sv += g * g;
     }
     se = block_sum_ap(se, red);
@@ -166,12 +168,12 @@ __global__ void __launch_bounds__(AP_THREADS) k_apply(const ApplyArgs a) {
 #pragma unroll
   for (int j = 0; j < AP_PER_THREAD; ++j) {
     const int i = (blockIdx.x * AP_PER_THREAD + j) * AP_THREADS + t;
-    if (i >= NUM_PARAMS) break;
+    if (i >= a.num_params) break;
     int seg = 0;
     bool live = true;
-    const float coef = i < ENCODER_END ? c_enc : (i < POLICY_END ? c_pol : c_val);
-    if (i >= P_LU_W0 && i < P_RD_W0) { seg = 1; live = live_lu; }
-    else if (i >= P_RD_W0 && i < POLICY_END) { seg = 2; live = live_rd; }
+    const float coef = i < a.encoder_end ? c_enc : (i < a.policy_end ? c_pol : c_val);
+    if (i >= a.lu_begin && i < a.rd_begin) { seg = 1; live = live_lu; }
+    else if (i >= a.rd_begin && i < a.policy_end) { seg = 2; live = live_rd; }
     if (!live) continue;
     const float g = __fmul_rn(a.grad[i], coef);
     float m = a.m[i], v = a.v[i];

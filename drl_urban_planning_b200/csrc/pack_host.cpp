@@ -100,7 +100,7 @@ const char* measure_one(const StateView& s, int n_cap, int e_cap, bool check_edg
     k = count_set(s.road_mask, 0, n);
     if (count_set(s.road_mask, n, n_cap)) return "road_mask marks a padded node";
   }
-  if (k > 65534) return "more than 65534 action candidates";
+  if (k > 32766) return "more than 32766 action candidates";
   *out = Counts{n, e, k, stage};
   return nullptr;
 }
@@ -472,7 +472,7 @@ const char* fill_one(const StateView& s, const GraphDesc& d, const BlobHeader& h
       tag = (uint32_t)(slot + 1) << 16;
       ++slot;
     }
-    adj[pos[u]++] = v | tag;
+    adj[pos[u]++] = v | tag | kAdjFirst;      // row owner u is the edge's FIRST endpoint (edge_index[j][0])
     adj[pos[v]++] = u | tag;
   }
   for (int a = 2 * e; a < adj_len; ++a) adj[a] = 0;

@@ -741,12 +741,12 @@ __device__ __forceinline__ float4 pull_backward(const GraphView& g, int q, float
       float2 ga0 = __ffma2_rn(h0.a, two, gsa), gb0 = __ffma2_rn(h0.b, two, gsb);
       float2 ga1 = __ffma2_rn(h1.a, two, gsa), gb1 = __ffma2_rn(h1.b, two, gsb);
       if (use_head) {
-        if (e0 >> 16) {
-          const F2x2 gh = ldp(g.ghead + (size_t)((e0 >> 16) - 1) * 16 + q * 4);
+        if ((e0 >> 16) & kAdjSlotMask) {
+          const F2x2 gh = ldp(g.ghead + (size_t)(((e0 >> 16) & kAdjSlotMask) - 1) * 16 + q * 4);
           ga0 = __ffma2_rn(gh.a, two, ga0); gb0 = __ffma2_rn(gh.b, two, gb0);
         }
-        if (e1 >> 16) {
-          const F2x2 gh = ldp(g.ghead + (size_t)((e1 >> 16) - 1) * 16 + q * 4);
+        if ((e1 >> 16) & kAdjSlotMask) {
+          const F2x2 gh = ldp(g.ghead + (size_t)(((e1 >> 16) & kAdjSlotMask) - 1) * 16 + q * 4);
           ga1 = __ffma2_rn(gh.a, two, ga1); gb1 = __ffma2_rn(gh.b, two, gb1);
         }
       }
@@ -760,8 +760,8 @@ __device__ __forceinline__ float4 pull_backward(const GraphView& g, int q, float
       const int k0 = e0 & 0xffffu;
       const F2x2 X0 = ldp(g.EPQ + k0 * 32 + offX), Y0 = ldp(g.EPQ + k0 * 32 + offY), h0 = ldp(g.H + k0 * 16 + q * 4);
       float2 ga0 = __ffma2_rn(h0.a, two, gsa), gb0 = __ffma2_rn(h0.b, two, gsb);
-      if (use_head && (e0 >> 16)) {
-        const F2x2 gh = ldp(g.ghead + (size_t)((e0 >> 16) - 1) * 16 + q * 4);
+      if (use_head && ((e0 >> 16) & kAdjSlotMask)) {
+        const F2x2 gh = ldp(g.ghead + (size_t)(((e0 >> 16) & kAdjSlotMask) - 1) * 16 + q * 4);
         ga0 = __ffma2_rn(gh.a, two, ga0); gb0 = __ffma2_rn(gh.b, two, gb0);
       }
       bwd_term<EXACT>(A.a, B.a, Y0.a, X0.a, ga0, u0, v0);
@@ -1068,7 +1068,7 @@ __device__ __forceinline__ float half_sum(float v, unsigned mask) {
 // padded logits: masked entries have probability exactly 0), outputs, PPO seeds and the logit gradients.
 template <bool TRAIN>
 __device__ __forceinline__ void softmax_seeds(const StepArgs& a, const BlobHeader& hd, const GraphView& g, float* sc,
-                                              float* gp, int lane) {
+                                              float* stats, int lane) {      // stats: the CTA's 8 statistics slots
   const int k = g.k, gid = g.gid;
   float lmax = -CUDART_INF_F;
   int lbest = 0x7fffffff;
@@ -1161,7 +1161,7 @@ __device__ __forceinline__ void softmax_seeds(const StepArgs& a, const BlobHeade
     }
     if (lane == 0) {
       sc[SC_GV] = 2.f * a.c_value * dv * a.inv_batch;
-      float* st = gp + G_STATS;
+      float* st = stats;
       st[0] += dv * dv; st[1] += surr; st[2] += negent; st[3] += 1.f; st[4] += in_ind;
       st[5] += g.stage == 0 ? 1.f : 0.f; st[6] += g.stage == 1 ? 1.f : 0.f;
       st[7] += (isfinite(V) && isfinite(logp) && isfinite(H)) ? 0.f : 1.f;
@@ -1460,7 +1460,7 @@ __device__ void graph_body(const StepArgs& a, const BlobHeader& hd, const GraphD
     }
     if (tid >= 256 && tid < 272) sV[V_GHC + tid - 256] = 0.f;
   }
-  if (warp == NW - 1) softmax_seeds<TRAIN>(a, hd, g, sc, gp, lane);
+  if (warp == NW - 1) softmax_seeds<TRAIN>(a, hd, g, sc, TRAIN ? gp + G_STATS : nullptr, lane);
   if constexpr (!TRAIN) return;
   __syncthreads();
   UPB_STAMP(10);
@@ -1950,7 +1950,12 @@ __device__ void fused_tail(const StepArgs& a, float* smem, unsigned stage_bits) 
         s4 += __ldcg(src + (size_t)(r + 16) * G_ROW); s5 += __ldcg(src + (size_t)(r + 20) * G_ROW);
         s6 += __ldcg(src + (size_t)(r + 24) * G_ROW); s7 += __ldcg(src + (size_t)(r + 28) * G_ROW);
       }
-      for (; r < nparts; r += 4) s0 += __ldcg(src + (size_t)r * G_ROW);
+      if (r < nparts) {     // the last (up to seven) rows of this thread: one more batch of loads in flight together
+        float t[7];
+#pragma unroll
+        for (int j = 0; j < 7; ++j) t[j] = r + 4 * j < nparts ? __ldcg(src + (size_t)(r + 4 * j) * G_ROW) : 0.f;
+        s0 += t[0]; s1 += t[1]; s2 += t[2]; s3 += t[3]; s4 += t[4]; s5 += t[5]; s6 += t[6];
+      }
       s = ((s0 + s1) + (s2 + s3)) + ((s4 + s5) + (s6 + s7));
     }
     s += __shfl_xor_sync(0xffffffffu, s, 1);

@@ -14,6 +14,7 @@
 #include "layout.h"
 #include "optim_kernels.cuh"
 #include "sgnn_kernel.cuh"
+#include "mlp_kernel.cuh"
 
 using namespace upb;
 
@@ -41,6 +42,15 @@ struct upb_ctx {
   long long* stamps = nullptr;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
   size_t prof_used = 0;
+  // rl-mlp ablation model: its own partial rows, scratch, Adam state and step counters (allocated on first use)
+  float* m_gpart = nullptr;
+  float* m_scratch = nullptr;
+  size_t m_scratch_stride = 0;
+  float* m_adam_m = nullptr;
+  float* m_adam_v = nullptr;
+  long long* m_steps = nullptr;
+  int m_steps_cur = 0;
+  bool m_clip_armed = true;
   // multi-GPU fused step (upb_peer_export / upb_peer_connect)
   float* xchg = nullptr;             // this rank's exchange buffer (sgnn_kernel.cuh: XCHG_FLOATS): slice sums by
                                      // [parity][source rank], then the per-slice flags
@@ -211,6 +221,11 @@ extern "C" void upb_destroy(upb_ctx* ctx) {
   cudaFree(ctx->steps);
   cudaFree(ctx->ticket);
   cudaFree(ctx->gridbar);
+  cudaFree(ctx->m_gpart);
+  cudaFree(ctx->m_scratch);
+  cudaFree(ctx->m_adam_m);
+  cudaFree(ctx->m_adam_v);
+  cudaFree(ctx->m_steps);
   for (int p = 0; p < (int)ctx->peer_ptrs.size(); ++p)
     if (p != ctx->rank && ctx->peer_ptrs[p]) cudaIpcCloseMemHandle(ctx->peer_ptrs[p]);
   cudaFree(ctx->peers_dev);
@@ -302,6 +317,8 @@ extern "C" int upb_apply(upb_ctx* ctx, float* params, const float* grad, void* s
   a.eps = ctx->cfg.adam_eps;
   a.clip_now = clip_now(ctx) ? 1 : 0;
   ctx->clip_armed = false;
+  a.num_params = NUM_PARAMS; a.encoder_end = ENCODER_END; a.policy_end = POLICY_END;
+  a.lu_begin = P_LU_W0; a.rd_begin = P_RD_W0; a.stat_offset = UPB_STAT_OFFSET;
   k_apply<<<AP_BLOCKS, AP_THREADS, 0, (cudaStream_t)stream>>>(a);
   ctx->launches += 1;
   UPB_CUDA(cudaGetLastError());
@@ -423,6 +440,157 @@ extern "C" int upb_peer_timeouts(upb_ctx* ctx, int64_t* count) {
 extern "C" int upb_next_step_fused(upb_ctx* ctx) {
   if (!ctx) return 0;
   return (!clip_now(ctx) && ctx->coop) ? 1 : 0;
+}
+
+// ---- rl-mlp ablation model ---------------------------------------------------------------------------------------------
+namespace {
+int mlp_init(upb_ctx* ctx) {
+  if (ctx->m_gpart) return UPB_OK;
+  ctx->m_scratch_stride = (mlp_scratch_floats(ctx->cfg.n_cap, ctx->cfg.e_cap) + 63) & ~size_t(63);
+  UPB_CUDA(cudaMalloc(&ctx->m_gpart, sizeof(float) * (size_t)ctx->grid * MG_ROW));
+  UPB_CUDA(cudaMalloc(&ctx->m_scratch, sizeof(float) * (size_t)ctx->grid * ctx->m_scratch_stride));
+  UPB_CUDA(cudaMalloc(&ctx->m_adam_m, sizeof(float) * M_NUM_PARAMS));
+  UPB_CUDA(cudaMalloc(&ctx->m_adam_v, sizeof(float) * M_NUM_PARAMS));
+  UPB_CUDA(cudaMalloc(&ctx->m_steps, sizeof(long long) * 8));
+  UPB_CUDA(cudaMemset(ctx->m_adam_m, 0, sizeof(float) * M_NUM_PARAMS));
+  UPB_CUDA(cudaMemset(ctx->m_adam_v, 0, sizeof(float) * M_NUM_PARAMS));
+  UPB_CUDA(cudaMemset(ctx->m_steps, 0, sizeof(long long) * 8));
+  UPB_CUDA(cudaMemset(ctx->m_scratch, 0, sizeof(float) * (size_t)ctx->grid * ctx->m_scratch_stride));
+  UPB_CUDA(cudaFuncSetAttribute(k_mlp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)M_SMEM_BYTES));
+  UPB_CUDA(cudaFuncSetAttribute(k_mlp<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)M_SMEM_BYTES));
+  UPB_CUDA(cudaDeviceSynchronize());
+  return UPB_OK;
+}
+StepArgs mlp_args(upb_ctx* ctx, const void* blob, const int32_t* ids, int count, const float* params,
+                  const float* actions) {
+  StepArgs a = base_args(ctx, blob, ids, count, params, actions);
+  a.gpart = ctx->m_gpart;
+  a.scratch = ctx->m_scratch;
+  a.scratch_stride = ctx->m_scratch_stride;
+  return a;
+}
+}  // namespace
+
+extern "C" int upb_mlp_forward(upb_ctx* ctx, const void* blob_dev, const int32_t* ids, int count, const float* params,
+                               const float* actions, float* value, float* log_prob, float* entropy, int32_t* greedy,
+                               void* stream) {
+  if (int rc = check_ctx(ctx, "mlp_forward")) return rc;
+  if (!blob_dev || !params || count < 0) return set_error(UPB_ERR_ARG, "mlp_forward: bad argument");
+  if (int rc = mlp_init(ctx)) return rc;
+  if (count == 0) return UPB_OK;
+  StepArgs a = mlp_args(ctx, blob_dev, ids, count, params, actions);
+  a.out_value = value; a.out_logp = log_prob; a.out_entropy = entropy; a.out_greedy = greedy;
+  const int grid = count < ctx->grid ? count : ctx->grid;
+  k_mlp<false><<<grid, MT, M_SMEM_BYTES, (cudaStream_t)stream>>>(a);
+  ctx->launches += 1;
+  UPB_CUDA(cudaGetLastError());
+  return UPB_OK;
+}
+
+extern "C" int upb_mlp_select_action(upb_ctx* ctx, const void* blob_dev, const int32_t* ids, int count,
+                                     const float* params, const float* uniforms, int32_t* action_index, void* stream) {
+  if (int rc = check_ctx(ctx, "mlp_select_action")) return rc;
+  if (!blob_dev || !params || !action_index || count < 0) return set_error(UPB_ERR_ARG, "mlp_select_action: bad argument");
+  if (int rc = mlp_init(ctx)) return rc;
+  if (count == 0) return UPB_OK;
+  StepArgs a = mlp_args(ctx, blob_dev, ids, count, params, nullptr);
+  if (uniforms) { a.uniforms = uniforms; a.out_sample = action_index; }
+  else a.out_greedy = action_index;
+  const int grid = count < ctx->grid ? count : ctx->grid;
+  k_mlp<false><<<grid, MT, M_SMEM_BYTES, (cudaStream_t)stream>>>(a);
+  ctx->launches += 1;
+  UPB_CUDA(cudaGetLastError());
+  return UPB_OK;
+}
+
+extern "C" int upb_mlp_ppo_grad(upb_ctx* ctx, const void* blob_dev, const int32_t* ids, int count, const float* params,
+                                const float* actions, const float* advantages, const float* returns,
+                                const float* fixed_log_probs, const float* exps, float inv_batch, float inv_ind,
+                                float* grad_out, void* stream) {
+  if (int rc = check_ctx(ctx, "mlp_ppo_grad")) return rc;
+  if (!blob_dev || !params || !actions || !advantages || !returns || !fixed_log_probs || !exps || !grad_out || count < 0)
+    return set_error(UPB_ERR_ARG, "mlp_ppo_grad: bad argument");
+  if (int rc = mlp_init(ctx)) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  StepArgs a = mlp_args(ctx, blob_dev, ids, count, params, actions);
+  a.adv = advantages; a.ret = returns; a.fixed_lp = fixed_log_probs; a.exps = exps;
+  a.inv_batch = inv_batch; a.inv_ind = inv_ind;
+  const int grid = count < ctx->grid ? count : ctx->grid;
+  if (grid > 0) {
+    const bool prof = prof_begin(ctx, s);
+    k_mlp<true><<<grid, MT, M_SMEM_BYTES, s>>>(a);
+    prof_end(ctx, s, prof);
+    ctx->launches += 1;
+  }
+  k_mlp_reduce<<<(MG_ROW + 255) / 256, 256, 0, s>>>(ctx->m_gpart, grid, grad_out);
+  ctx->launches += 1;
+  UPB_CUDA(cudaGetLastError());
+  return UPB_OK;
+}
+
+extern "C" int upb_mlp_apply(upb_ctx* ctx, float* params, const float* grad, void* stream) {
+  if (int rc = check_ctx(ctx, "mlp_apply")) return rc;
+  if (!params || !grad) return set_error(UPB_ERR_ARG, "mlp_apply: bad argument");
+  if (int rc = mlp_init(ctx)) return rc;
+  ApplyArgs a;
+  a.params = params; a.grad = grad; a.m = ctx->m_adam_m; a.v = ctx->m_adam_v;
+  a.steps_in = ctx->m_steps + 4 * ctx->m_steps_cur;
+  a.steps_out = ctx->m_steps + 4 * (1 - ctx->m_steps_cur);
+  ctx->m_steps_cur = 1 - ctx->m_steps_cur;
+  a.lr = ctx->cfg.lr; a.beta1 = ctx->cfg.beta1; a.beta2 = ctx->cfg.beta2; a.eps = ctx->cfg.adam_eps;
+  a.clip_now = (ctx->cfg.clip_mode == UPB_CLIP_ALWAYS || (ctx->cfg.clip_mode == UPB_CLIP_REFERENCE && ctx->m_clip_armed)) ? 1 : 0;
+  ctx->m_clip_armed = false;
+  a.num_params = M_NUM_PARAMS; a.encoder_end = M_ENCODER_END; a.policy_end = M_POLICY_END;
+  a.lu_begin = M_LU_W0; a.rd_begin = M_RD_W0; a.stat_offset = UPB_MLP_STAT_OFFSET;
+  k_apply<<<AP_BLOCKS, AP_THREADS, 0, (cudaStream_t)stream>>>(a);
+  ctx->launches += 1;
+  UPB_CUDA(cudaGetLastError());
+  return UPB_OK;
+}
+
+namespace {
+int read_losses_at(upb_ctx* ctx, const float* stats_dev, float* out4_host, cudaStream_t s) {
+  UPB_CUDA(cudaMemcpyAsync(ctx->host_pinned, stats_dev, sizeof(float) * 8, cudaMemcpyDeviceToHost, s));
+  UPB_CUDA(cudaStreamSynchronize(s));
+  const float* st = ctx->host_pinned;
+  const float nB = st[3] > 0.f ? st[3] : 1.f, nI = st[4] > 0.f ? st[4] : 1.f;
+  const float value_loss = st[0] / nB, surr = st[1] / nI, ent = st[2] / nI;
+  out4_host[0] = surr + ctx->cfg.value_pred_coef * value_loss + ctx->cfg.entropy_coef * ent;
+  out4_host[1] = value_loss;
+  out4_host[2] = surr;
+  out4_host[3] = ent;
+  return UPB_OK;
+}
+}  // namespace
+
+extern "C" int upb_mlp_read_losses(upb_ctx* ctx, const float* grad, float* out4_host, void* stream) {
+  if (int rc = check_ctx(ctx, "mlp_read_losses")) return rc;
+  if (!grad || !out4_host) return set_error(UPB_ERR_ARG, "mlp_read_losses: bad argument");
+  return read_losses_at(ctx, grad + UPB_MLP_STAT_OFFSET, out4_host, (cudaStream_t)stream);
+}
+
+extern "C" int upb_mlp_get_opt_state(upb_ctx* ctx, float* m_host, float* v_host, int64_t* steps4_host) {
+  if (int rc = check_ctx(ctx, "mlp_get_opt_state")) return rc;
+  if (int rc = mlp_init(ctx)) return rc;
+  UPB_CUDA(cudaDeviceSynchronize());
+  if (m_host) UPB_CUDA(cudaMemcpy(m_host, ctx->m_adam_m, sizeof(float) * M_NUM_PARAMS, cudaMemcpyDeviceToHost));
+  if (v_host) UPB_CUDA(cudaMemcpy(v_host, ctx->m_adam_v, sizeof(float) * M_NUM_PARAMS, cudaMemcpyDeviceToHost));
+  if (steps4_host)
+    UPB_CUDA(cudaMemcpy(steps4_host, ctx->m_steps + 4 * ctx->m_steps_cur, sizeof(long long) * 4, cudaMemcpyDeviceToHost));
+  return UPB_OK;
+}
+
+extern "C" int upb_mlp_set_opt_state(upb_ctx* ctx, const float* m_host, const float* v_host, const int64_t* steps4_host) {
+  if (int rc = check_ctx(ctx, "mlp_set_opt_state")) return rc;
+  if (int rc = mlp_init(ctx)) return rc;
+  UPB_CUDA(cudaDeviceSynchronize());
+  if (m_host) UPB_CUDA(cudaMemcpy(ctx->m_adam_m, m_host, sizeof(float) * M_NUM_PARAMS, cudaMemcpyHostToDevice));
+  if (v_host) UPB_CUDA(cudaMemcpy(ctx->m_adam_v, v_host, sizeof(float) * M_NUM_PARAMS, cudaMemcpyHostToDevice));
+  if (steps4_host) {
+    UPB_CUDA(cudaMemcpy(ctx->m_steps + 4 * ctx->m_steps_cur, steps4_host, sizeof(long long) * 4, cudaMemcpyHostToDevice));
+    ctx->m_clip_armed = steps4_host[0] == 0;
+  }
+  return UPB_OK;
 }
 
 extern "C" int upb_read_losses(upb_ctx* ctx, const float* grad, float* out4_host, void* stream) {

@@ -65,7 +65,18 @@ def bind_host_to_gpu_node(device=None):
 class Engine:
     def __init__(self, device, n_cap: int, e_cap: int, lr: float = 4e-4, betas=(0.9, 0.999), eps: float = 1e-5,
                  clip_epsilon: float = 0.2, value_pred_coef: float = 0.5, entropy_coef: float = 0.01,
-                 clip_mode: int = _lib.CLIP_REFERENCE, grid_limit: int = 0, max_graphs: int = 1 << 20):
+                 clip_mode: int = _lib.CLIP_REFERENCE, grid_limit: int = 0, max_graphs: int = 1 << 20,
+                 model: str = "sgnn"):
+        if model not in ("sgnn", "mlp"):
+            raise ValueError("model must be 'sgnn' (rl-sgnn) or 'mlp' (rl-mlp ablation)")
+        # model = "mlp": the reference's rl-mlp ablation (create_mlp_model); every call below then runs the k_mlp kernels
+        # on that model's flat layout.  The fused single-launch step and the in-kernel peer exchange exist for the SGNN
+        # only; the rl-mlp step is upb_mlp_ppo_grad (+ all-reduce) + upb_mlp_apply.
+        self.model = model
+        self._p = "upb_mlp_" if model == "mlp" else "upb_"
+        self.num_params = _lib.UPB_MLP_NUM_PARAMS if model == "mlp" else _lib.UPB_NUM_PARAMS
+        self.grad_stride = _lib.UPB_MLP_GRAD_STRIDE if model == "mlp" else _lib.UPB_GRAD_STRIDE
+        self.stat_offset = _lib.UPB_MLP_STAT_OFFSET if model == "mlp" else _lib.UPB_STAT_OFFSET
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise _lib.UpbError("the update path runs on a CUDA device only (no CPU fallback)")
@@ -114,14 +125,16 @@ class Engine:
             actions = _f32(actions, dev)
             assert actions.numel() == 2 * n, "actions must be (count, 2) like the reference's"
         cnt = n if ids is None else int(ids.numel())
-        _lib.check(_lib.lib().upb_forward(self._ctx, blob.dev_ptr(), _ptr(ids), cnt, params.data_ptr(),
-                                          _ptr(actions), value.data_ptr(), logp.data_ptr(), ent.data_ptr(),
-                                          _ptr(greedy), self._stream()), "upb_forward")
+        assert params.numel() == self.num_params, "flat parameter vector of the wrong model"
+        _lib.check(getattr(_lib.lib(), self._p + "forward")(self._ctx, blob.dev_ptr(), _ptr(ids), cnt, params.data_ptr(),
+                                                           _ptr(actions), value.data_ptr(), logp.data_ptr(),
+                                                           ent.data_ptr(), _ptr(greedy), self._stream()),
+                   self._p + "forward")
         return (value, logp, ent, greedy) if want_greedy else (value, logp, ent)
 
     # ------------------------------------------------------------------ training step pieces
     def new_grad_buffer(self) -> torch.Tensor:
-        return torch.zeros(_lib.UPB_GRAD_STRIDE, dtype=torch.float32, device=self.device)
+        return torch.zeros(self.grad_stride, dtype=torch.float32, device=self.device)
 
     def ppo_grad(self, blob: PackedGraphs, params: torch.Tensor, actions: torch.Tensor, advantages: torch.Tensor,
                  returns: torch.Tensor, fixed_log_probs: torch.Tensor, exps: torch.Tensor, inv_batch: float,
@@ -134,11 +147,11 @@ class Engine:
         if out is None:
             out = self.new_grad_buffer()
         cnt = blob.count if ids is None else int(ids.numel())
-        _lib.check(_lib.lib().upb_ppo_grad(
+        _lib.check(getattr(_lib.lib(), self._p + "ppo_grad")(
             self._ctx, blob.dev_ptr(), _ptr(ids), cnt, params.data_ptr(), _f32(actions, dev).data_ptr(),
             _f32(advantages, dev).data_ptr(), _f32(returns, dev).data_ptr(), _f32(fixed_log_probs, dev).data_ptr(),
             _f32(exps, dev).data_ptr(), float(inv_batch), float(inv_ind), out.data_ptr(), self._stream()),
-            "upb_ppo_grad")
+            self._p + "ppo_grad")
         return out
 
     def ppo_step(self, blob: PackedGraphs, params: torch.Tensor, actions: torch.Tensor, advantages: torch.Tensor,
@@ -151,6 +164,11 @@ class Engine:
         dev = self.device
         if out is None:
             out = self.new_grad_buffer()
+        if self.model == "mlp":       # two-call form (no fused tail for the ablation model)
+            self.ppo_grad(blob, params, actions, advantages, returns, fixed_log_probs, exps, inv_batch, inv_ind,
+                          ids=ids, out=out)
+            self.apply(params, out)
+            return out
         cnt = blob.count if ids is None else int(ids.numel())
         _lib.check(_lib.lib().upb_ppo_step(
             self._ctx, blob.dev_ptr(), _ptr(ids), cnt, params.data_ptr(), _f32(actions, dev).data_ptr(),
@@ -171,9 +189,9 @@ class Engine:
             u = _f32(uniforms, self.device).reshape(-1)
             if u.numel() != blob.count:
                 raise ValueError("uniforms must hold one value per graph of the blob")
-        _lib.check(_lib.lib().upb_select_action(self._ctx, blob.dev_ptr(), _ptr(ids), cnt, params.data_ptr(),
-                                                None if u is None else u.data_ptr(), out.data_ptr(), self._stream()),
-                   "upb_select_action")
+        _lib.check(getattr(_lib.lib(), self._p + "select_action")(
+            self._ctx, blob.dev_ptr(), _ptr(ids), cnt, params.data_ptr(), None if u is None else u.data_ptr(),
+            out.data_ptr(), self._stream()), self._p + "select_action")
         return out
 
     # ---- multi-GPU fused step (include/upb200.h: upb_peer_*) -----------------------------------------------------
@@ -194,13 +212,15 @@ class Engine:
         return int(n.value)
 
     def next_step_fused(self) -> bool:
-        return bool(_lib.lib().upb_next_step_fused(self._ctx))
+        return self.model == "sgnn" and bool(_lib.lib().upb_next_step_fused(self._ctx))
 
     def connect_peers(self, process_group=None) -> bool:
         """Exchange the ranks' IPC handles over `process_group` (NCCL) and map the peers' exchange buffers.  Collective;
         returns True on every rank or False on every rank (then the NCCL all-reduce path stays in use)."""
         import torch.distributed as dist
         world, rank = dist.get_world_size(process_group), dist.get_rank(process_group)
+        if self.model != "sgnn":
+            return False
         if world < 2 or getattr(self, "peers", 1) > 1:
             return getattr(self, "peers", 1) > 1
         ok = torch.ones(1, dtype=torch.int32, device=self.device)
@@ -223,11 +243,13 @@ class Engine:
         return self.peers_ok
 
     def apply(self, params: torch.Tensor, grad: torch.Tensor) -> None:
-        _lib.check(_lib.lib().upb_apply(self._ctx, params.data_ptr(), grad.data_ptr(), self._stream()), "upb_apply")
+        _lib.check(getattr(_lib.lib(), self._p + "apply")(self._ctx, params.data_ptr(), grad.data_ptr(), self._stream()),
+                   self._p + "apply")
 
     def read_losses(self, grad: torch.Tensor) -> Tuple[float, float, float, float]:
         out = (C.c_float * 4)()
-        _lib.check(_lib.lib().upb_read_losses(self._ctx, grad.data_ptr(), out, self._stream()), "upb_read_losses")
+        _lib.check(getattr(_lib.lib(), self._p + "read_losses")(self._ctx, grad.data_ptr(), out, self._stream()),
+                   self._p + "read_losses")
         return tuple(float(x) for x in out)
 
     def gae(self, rewards: torch.Tensor, masks: torch.Tensor, values: torch.Tensor, gamma: float, tau: float):
@@ -242,11 +264,11 @@ class Engine:
 
     # ------------------------------------------------------------------ optimiser state
     def get_opt_state(self):
-        m = np.zeros(_lib.UPB_NUM_PARAMS, np.float32)
-        v = np.zeros(_lib.UPB_NUM_PARAMS, np.float32)
+        m = np.zeros(self.num_params, np.float32)
+        v = np.zeros(self.num_params, np.float32)
         steps = np.zeros(4, np.int64)
-        _lib.check(_lib.lib().upb_get_opt_state(self._ctx, m.ctypes.data, v.ctypes.data, steps.ctypes.data),
-                   "upb_get_opt_state")
+        _lib.check(getattr(_lib.lib(), self._p + "get_opt_state")(self._ctx, m.ctypes.data, v.ctypes.data,
+                                                                 steps.ctypes.data), self._p + "get_opt_state")
         return m, v, steps
 
     def set_opt_state(self, m: np.ndarray, v: np.ndarray, steps: np.ndarray, rearm_first_step_clip: bool = False
@@ -254,9 +276,10 @@ class Engine:
         m = np.ascontiguousarray(m, np.float32)
         v = np.ascontiguousarray(v, np.float32)
         steps = np.ascontiguousarray(steps, np.int64)
-        _lib.check(_lib.lib().upb_set_opt_state(self._ctx, m.ctypes.data, v.ctypes.data, steps.ctypes.data),
-                   "upb_set_opt_state")
-        if rearm_first_step_clip:
+        assert m.size == self.num_params and v.size == self.num_params
+        _lib.check(getattr(_lib.lib(), self._p + "set_opt_state")(self._ctx, m.ctypes.data, v.ctypes.data,
+                                                                 steps.ctypes.data), self._p + "set_opt_state")
+        if rearm_first_step_clip and self.model == "sgnn":
             _lib.check(_lib.lib().upb_rearm_clip(self._ctx), "upb_rearm_clip")
 
     def profile(self, enable: bool) -> None:

@@ -117,24 +117,29 @@ def _states_on_cuda(x) -> bool:
 class _EngineMixin:
     """CUDA dispatch shared by the policy and value modules: flat parameter snapshot + engine + packing."""
 
+    def _layout(self):
+        return PL.MLP if getattr(self.shared_net, "model_kind", "sgnn") == "mlp" else PL.SGNN
+
     def _flat_params(self, device):
         named = {}
         sn = dict(self.shared_net.named_parameters())
         own = dict(self.named_parameters())
-        for s in PL.SLOTS.values():
+        slots = self._layout().slots
+        for s in slots.values():
             if s.owner == "enc":
                 named[s.name] = sn[s.key]
             elif s.key in own:
                 named[s.name] = own[s.key]
             else:
                 named[s.name] = getattr(self, "_peer_params")()[s.key]
-        return torch.cat([named[s.name].detach().reshape(-1).to(device, torch.float32) for s in PL.SLOTS.values()])
+        return torch.cat([named[s.name].detach().reshape(-1).to(device, torch.float32) for s in slots.values()])
 
     def _engine(self, device):
         from .engine import Engine
         eng = getattr(self.shared_net, "_upb_engine", None)
         if eng is None or eng.device != torch.device(device):
-            eng = Engine(device, self.shared_net.max_num_nodes, self.shared_net.max_num_edges)
+            eng = Engine(device, self.shared_net.max_num_nodes, self.shared_net.max_num_edges,
+                         model=getattr(self.shared_net, "model_kind", "sgnn"))
             self.shared_net._upb_engine = eng
         return eng
 

@@ -162,3 +162,93 @@ def default_init(seed: int) -> np.ndarray:
             bound = 1.0 / np.sqrt(fan_in)
             named[s.name] = rng.uniform(-bound, bound, s.shape)
     return flatten(named)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# rl-mlp ablation (`create_mlp_model`, reference urban_planning/models/model.py:22-33, state_encoder.py:217-308): no
+# message passing and no attention; the value features are [h_num | mean h_nodes | mean h_edges | stage] = 51 wide.
+VALUE_IN_MLP = 2 * GCN_DIM + NUM_HIDDEN[-1] + STAGE_DIM        # 51 (state_encoder.py:236)
+_MLP_TABLE: List[Tuple[str, str, str, Tuple[int, ...]]] = [
+    ("num_w0", "numerical_feature_encoder.linear_0.weight", "enc", (64, 52)),
+    ("num_b0", "numerical_feature_encoder.linear_0.bias", "enc", (64,)),
+    ("num_w1", "numerical_feature_encoder.linear_1.weight", "enc", (16, 64)),
+    ("num_b1", "numerical_feature_encoder.linear_1.bias", "enc", (16,)),
+    ("enc_w", "node_encoder.weight", "enc", (16, 23)),
+    ("enc_b", "node_encoder.bias", "enc", (16,)),
+    ("lu_w0", "policy_land_use_head.land_use_linear_0.weight", "pol", (32, 64)),
+    ("lu_b0", "policy_land_use_head.land_use_linear_0.bias", "pol", (32,)),
+    ("lu_w1", "policy_land_use_head.land_use_linear_1.weight", "pol", (1, 32)),
+    ("road_w0", "policy_road_head.road_linear_0.weight", "pol", (32, 16)),
+    ("road_b0", "policy_road_head.road_linear_0.bias", "pol", (32,)),
+    ("road_w1", "policy_road_head.road_linear_1.weight", "pol", (1, 32)),
+    ("val_w0", "value_head.linear_0.weight", "val", (32, VALUE_IN_MLP)),
+    ("val_b0", "value_head.linear_0.bias", "val", (32,)),
+    ("val_w1", "value_head.linear_1.weight", "val", (32, 32)),
+    ("val_b1", "value_head.linear_1.bias", "val", (32,)),
+    ("val_w2", "value_head.linear_2.weight", "val", (1, 32)),
+    ("val_b2", "value_head.linear_2.bias", "val", (1,)),
+]
+
+
+class Layout:
+    """A flat parameter layout (table of tensors in `ActorCritic.parameters()` order) with the conversions above."""
+
+    def __init__(self, table):
+        self.slots: "OrderedDict[str, Slot]" = OrderedDict()
+        off = 0
+        for name, key, owner, shape in table:
+            sl = Slot(name, key, owner, shape, off)
+            self.slots[name] = sl
+            off += sl.size
+        self.num_params = off
+        self.encoder_end = self.slots["lu_w0"].offset
+        self.policy_end = self.slots["val_w0"].offset
+
+    def flatten(self, named) -> np.ndarray:
+        flat = np.zeros(self.num_params, dtype=np.float32)
+        for sl in self.slots.values():
+            flat[sl.offset:sl.offset + sl.size] = np.asarray(named[sl.name], dtype=np.float32).reshape(-1)
+        return flat
+
+    def unflatten(self, flat) -> Dict[str, np.ndarray]:
+        flat = np.asarray(flat)
+        return {sl.name: flat[sl.offset:sl.offset + sl.size].reshape(sl.shape) for sl in self.slots.values()}
+
+    def from_state_dict(self, sd) -> np.ndarray:
+        named = {}
+        for sl in self.slots.values():
+            v = sd[state_dict_keys(sl)[0]]
+            named[sl.name] = v.detach().cpu().numpy() if hasattr(v, "detach") else np.asarray(v)
+        return self.flatten(named)
+
+    def to_state_dict(self, flat):
+        named = self.unflatten(np.asarray(flat, dtype=np.float32))
+        actor, value = OrderedDict(), OrderedDict()
+        for sl in self.slots.values():
+            for k in state_dict_keys(sl):
+                (actor if k.startswith("actor_net.") else value)[k] = named[sl.name].copy()
+        out = OrderedDict()
+        out.update(actor)
+        out.update(value)
+        return out
+
+    def default_init(self, seed: int) -> np.ndarray:
+        """nn.Linear default init (U(+-1/sqrt(fan_in)) for weight and bias) from a numpy stream."""
+        rng = np.random.default_rng(seed)
+        named, fan = {}, {}
+        for sl in self.slots.values():
+            if len(sl.shape) == 2:
+                fan[sl.name[:-2] if sl.name[-2] == "w" else sl.name] = sl.shape[1]
+        for sl in self.slots.values():
+            if len(sl.shape) == 2:
+                bound = 1.0 / np.sqrt(sl.shape[1])
+            else:
+                w = sl.name.replace("_b", "_w")
+                bound = 1.0 / np.sqrt(self.slots[w].shape[1])
+            named[sl.name] = rng.uniform(-bound, bound, sl.shape)
+        return self.flatten(named)
+
+
+SGNN = Layout(_TABLE)
+MLP = Layout(_MLP_TABLE)
+assert SGNN.num_params == NUM_PARAMS and MLP.num_params == 10257

@@ -36,16 +36,17 @@ class PPOUpdater:
                  clip_epsilon: float = 0.2, value_pred_coef: float = 0.5, entropy_coef: float = 0.01,
                  gamma: float = 1.0, tau: float = 0.0, opt_num_epochs: int = 4, mini_batch_size: int = 256,
                  clip_mode: int = _lib.CLIP_REFERENCE, process_group="auto", pack_threads: int = 0,
-                 use_peers: bool = True, batch_stage: bool = False):
+                 use_peers: bool = True, batch_stage: bool = False, model: str = "sgnn"):
         self.device = torch.device(device)
         self.engine = Engine(self.device, n_cap, e_cap, lr=lr, eps=eps, clip_epsilon=clip_epsilon,
-                             value_pred_coef=value_pred_coef, entropy_coef=entropy_coef, clip_mode=clip_mode)
+                             value_pred_coef=value_pred_coef, entropy_coef=entropy_coef, clip_mode=clip_mode,
+                             model=model)
         self.device = self.engine.device
         if isinstance(flat_params, torch.Tensor):
             self.params = flat_params.detach().to(self.device, torch.float32).contiguous().clone()
         else:
             self.params = torch.as_tensor(np.asarray(flat_params, np.float32), device=self.device).clone()
-        assert self.params.numel() == _lib.UPB_NUM_PARAMS
+        assert self.params.numel() == self.engine.num_params
         self.gamma, self.tau = gamma, tau
         self.opt_num_epochs, self.mini_batch_size = opt_num_epochs, mini_batch_size
         self.value_pred_coef, self.entropy_coef = value_pred_coef, entropy_coef
@@ -160,7 +161,7 @@ class PPOUpdater:
         graphs, `global_ind` of which have exps != 0): urban_planning_agent.py:322-337."""
         args = (self.blob, self.params, self.actions, self.advantages, self.returns, self.fixed_log_probs, self.exps,
                 1.0 / max(global_batch, 1), 1.0 / max(global_ind, 1))
-        if self.world == 1 or (self.fused_exchange and self.engine.next_step_fused()):
+        if self.engine.model == "sgnn" and (self.world == 1 or (self.fused_exchange and self.engine.next_step_fused())):
             # one launch: gradient, reduction (over the ranks too, through peer memory), Adam
             self.engine.ppo_step(*args, ids=ids, out=self.grad)
         else:
@@ -190,7 +191,7 @@ class PPOUpdater:
         # straight into their own row (no per-step device copy), read back once per epoch
         ring = getattr(self, "_grad_ring", None)
         if ring is None or ring.shape[0] < max(nb, 1):
-            ring = torch.zeros(max(nb, 1), _lib.UPB_GRAD_STRIDE, dtype=torch.float32, device=self.device)
+            ring = torch.zeros(max(nb, 1), self.engine.grad_stride, dtype=torch.float32, device=self.device)
             self._grad_ring = ring
         totals = np.zeros(4)
 
@@ -218,7 +219,8 @@ class PPOUpdater:
             # broadcast on the stream, which would wait for them)
             if epoch + 1 < self.opt_num_epochs and self.world == 1:
                 cur = prepare(order)
-            stats_all = ring[:nb, _lib.UPB_STAT_OFFSET:_lib.UPB_STAT_OFFSET + 16]
+            so = self.engine.stat_offset
+            stats_all = ring[:nb, so:so + 16]
             st = stats_all.cpu().numpy().astype(np.float64)                            # one sync per epoch
             nB, nI = np.maximum(st[:, 3], 1), np.maximum(st[:, 4], 1)
             vl, sl_, el = st[:, 0] / nB, st[:, 1] / nI, st[:, 2] / nI

@@ -40,6 +40,11 @@ extern "C" {
  *   [3] #graphs                [4] #graphs in ind                          [5] #graphs stage land_use
  *   [6] #graphs stage road     [7] #non-finite per-graph results (NaN guard)            */
 
+/* rl-mlp ablation model (create_mlp_model, urban_planning/models/model.py:22-33): its own flat layout, 18 tensors */
+#define UPB_MLP_NUM_PARAMS 10257
+#define UPB_MLP_STAT_OFFSET 10260
+#define UPB_MLP_GRAD_STRIDE 10288   /* 10,257 gradients, 3 pad, UPB_STAT_COUNT statistics (same meaning as above) */
+
 typedef enum {
   UPB_OK = 0,
   UPB_ERR_ARG = -1,        /* bad argument */
@@ -167,6 +172,25 @@ int upb_next_step_fused(upb_ctx* ctx);
  * stale peer data is ever applied; the count is sticky.  Non-zero means the ranks are out of sync: stop and restore a
  * checkpoint.  Synchronises the device (PPOUpdater checks it once per epoch). */
 int upb_peer_timeouts(upb_ctx* ctx, int64_t* count);
+
+/* ---- rl-mlp ablation (`train.py --agent rl-mlp`; MLPStateEncoder, urban_planning/models/state_encoder.py:217-308) ----
+ * Same blob, same per-sample arrays and the same meaning of every argument as upb_forward / upb_ppo_grad / upb_apply,
+ * on the MLP model's flat layout (UPB_MLP_*): params / grad are f32[UPB_MLP_NUM_PARAMS] / f32[UPB_MLP_GRAD_STRIDE].  The
+ * context keeps a separate set of Adam moments and step counters for this model (upb_mlp_get/set_opt_state).  The step
+ * is always the two-call form (upb_mlp_ppo_grad, optional all-reduce, upb_mlp_apply). */
+int upb_mlp_forward(upb_ctx* ctx, const void* blob_dev, const int32_t* ids, int count, const float* params,
+                    const float* actions, float* value, float* log_prob, float* entropy, int32_t* greedy,
+                    void* stream);
+int upb_mlp_select_action(upb_ctx* ctx, const void* blob_dev, const int32_t* ids, int count, const float* params,
+                          const float* uniforms, int32_t* action_index, void* stream);
+int upb_mlp_ppo_grad(upb_ctx* ctx, const void* blob_dev, const int32_t* ids, int count, const float* params,
+                     const float* actions, const float* advantages, const float* returns,
+                     const float* fixed_log_probs, const float* exps, float inv_batch, float inv_ind,
+                     float* grad_out, void* stream);
+int upb_mlp_apply(upb_ctx* ctx, float* params, const float* grad, void* stream);
+int upb_mlp_read_losses(upb_ctx* ctx, const float* grad, float* out4_host, void* stream);
+int upb_mlp_get_opt_state(upb_ctx* ctx, float* m_host, float* v_host, int64_t* steps4_host);
+int upb_mlp_set_opt_state(upb_ctx* ctx, const float* m_host, const float* v_host, const int64_t* steps4_host);
 
 /* the 4 scalars the reference logs per minibatch (urban_planning_agent.py:338-345), from a gradient buffer:
  * out4 = {loss, value_loss, surr_loss, entropy_loss}.  Synchronises `stream`. */

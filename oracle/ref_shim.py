@@ -79,3 +79,14 @@ def build_reference_model(max_num_nodes: int, max_num_edges: int, seed: int):
     torch.manual_seed(seed)
     policy_net, value_net = create_sgnn_model(DuckCfg(max_num_nodes, max_num_edges), DuckAgent())
     return policy_net, value_net, ActorCritic(policy_net, value_net)
+
+
+def build_reference_mlp_model(max_num_nodes: int, max_num_edges: int, seed: int):
+    """(policy_net, value_net, actor_critic) of the rl-mlp ablation, built by the reference's `create_mlp_model`
+    (urban_planning/models/model.py:22-33) under `seed`."""
+    install()
+    import torch
+    from urban_planning.models.model import create_mlp_model, ActorCritic
+    torch.manual_seed(seed)
+    policy_net, value_net = create_mlp_model(DuckCfg(max_num_nodes, max_num_edges), DuckAgent())
+    return policy_net, value_net, ActorCritic(policy_net, value_net)

@@ -56,8 +56,8 @@ def check_blob(states, blob):
             tagged = {}
             for i_ in range(n):
                 for a in adj[rp[i_]:rp[i_ + 1]]:
-                    if a >> 16:
-                        tagged.setdefault(int(a >> 16) - 1, []).append((i_, int(a & 0xffff)))
+                    if (a >> 16) & 0x7fff:
+                        tagged.setdefault(int((a >> 16) & 0x7fff) - 1, []).append((i_, int(a & 0xffff)))
             assert sorted(tagged) == list(range(k))
             for s, ends in tagged.items():
                 u, v = int(ei[idx[s], 0]), int(ei[idx[s], 1])
@@ -65,7 +65,10 @@ def check_blob(states, blob):
         else:
             idx = np.flatnonzero(rm)
             assert np.array_equal(cidx, idx) and np.array_equal(cuv, idx)
-            assert not (adj >> 16).any()
+            assert not ((adj >> 16) & 0x7fff).any()
+        # bit 31: the row's node is the edge's FIRST endpoint -> exactly the directed entries (u -> v) of the edge list
+        first = sorted((i_, int(a & 0xffff)) for i_ in range(n) for a in adj[rp[i_]:rp[i_ + 1]] if a >> 31)
+        assert first == sorted((int(u), int(v)) for u, v in ei[:e])
     info = blob.info
     assert np.array_equal(info[:, 0], [int(s[4].sum()) for s in states])
 
