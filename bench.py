@@ -220,11 +220,15 @@ def main():
                          "sharded over the GPUs, walked in global minibatches of 256*N")
     ap.add_argument("--iter-states", type=int, default=25000,
                     help="e2e_iteration leg (N=1): rollout states of one whole update_params iteration (0 = skip)")
+    ap.add_argument("--tiles", default="f32", choices=["f32", "bf16"],
+                    help="bf16: the labelled NON-PARITY build with bf16-rounded single-pass tensor-core tiles (configs[2])")
     ap.add_argument("--padded-gpu", action="store_true",
                     help="also time the padded eager PyTorch dataflow (reference layout, oracle/_ref or port) on this GPU: "
                          "the padded-layout comparator of configs[4]")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    if args.tiles == "bf16":
+        os.environ["UPB_LIB"] = os.path.join(ROOT, "drl_urban_planning_b200", "libupb200_bf16.so")
     if args.impl == "reference":
         return run_reference(args)
 
@@ -564,7 +568,9 @@ def main():
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-            "scaling": "strong" if args.mode == "strong" else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "scaling": "strong" if args.mode == "strong" else "weak", "vs_baseline": None,
+            "dtype": "f32" if args.tiles == "f32" else "f32 with bf16-rounded single-pass tensor-core tiles (NOT parity-grade)",
+            "data": "synthetic",
             "config": {"workload": f"{workload_name(args)} (cfg {workload_name(args)}), PPO minibatch update, {BATCH} rollout graphs per GPU "
                                    f"per step, caps {blob.n_cap}/{blob.e_cap}, mean n={info[:, 0].mean():.0f} e={info[:, 1].mean():.0f}"
                                    + (", 8192-graph buffer sharded over the GPUs" if args.mode == "buffer" else ""),

@@ -7,7 +7,8 @@ import os
 from typing import Optional
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libupb200.so")
+# UPB_LIB selects another build of the same ABI (bench.py --tiles bf16 -> libupb200_bf16.so, the labelled non-parity variant)
+LIB_PATH = os.environ.get("UPB_LIB") or os.path.join(HERE, "libupb200.so")
 
 UPB_NUM_PARAMS = 13729
 UPB_GRAD_STRIDE = 13760

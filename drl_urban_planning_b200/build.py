@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libupb200.so")
 SOURCES = ["upb200.cu", "pack_host.cpp", "errors.cpp"]
-DEPS = SOURCES + ["sgnn_kernel.cuh", "optim_kernels.cuh", "layout.h", "blob.h", "errors.h",
+DEPS = SOURCES + ["sgnn_kernel.cuh", "mlp_kernel.cuh", "optim_kernels.cuh", "layout.h", "blob.h", "errors.h",
                   os.path.join("..", "..", "include", "upb200.h")]
 
 
@@ -49,6 +49,22 @@ def build_pyptr(force: bool = False) -> str:
     if res.returncode != 0:
         raise RuntimeError("gcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
     return PYPTR
+
+
+LIB_BF16 = os.path.join(HERE, "libupb200_bf16.so")
+
+
+def build_bf16_variant(force: bool = False) -> str:
+    """The labelled NON-PARITY variant with bf16-rounded, single-pass tensor-core tiles (bench.py --tiles bf16)."""
+    if not force and os.path.exists(LIB_BF16) and all(
+            os.path.getmtime(os.path.join(CSRC, d)) <= os.path.getmtime(LIB_BF16) for d in DEPS):
+        return LIB_BF16
+    cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-DUPB_TILE_BF16",
+           "-Xcompiler", "-fPIC,-O3,-pthread", "-shared", "-o", LIB_BF16] + [os.path.join(CSRC, s) for s in SOURCES]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+    return LIB_BF16
 
 
 def build_library(force: bool = False, verbose: bool = False) -> str:

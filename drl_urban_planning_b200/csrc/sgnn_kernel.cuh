@@ -537,6 +537,23 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], uint32_t a0, uint32_t a1
 }
 // one k-tile (8 columns) of a 16-row A tile held as four floats (rows g, g+8; tile columns t, t+4) times a B fragment
 // given as hi/lo pairs
+#ifdef UPB_TILE_BF16
+// NON-PARITY build (BASELINE.json configs[2] "fp32 vs bf16 MLP tiles", libupb200_bf16.so): the tensor-core tiles take
+// their operands rounded to bfloat16 (8-bit mantissa) and run ONE pass instead of the three of the 3xTF32 scheme.  A
+// bf16 value is exactly representable in TF32, so the m16n8k8 TF32 instruction computes the bf16 x bf16 -> fp32 product
+// exactly; results no longer meet the 1e-4 parity bar and bench.py labels the line accordingly.
+__device__ __forceinline__ uint32_t bf16_round(float x) {
+  uint32_t u = __float_as_uint(x);
+  u += 0x7fffu + ((u >> 16) & 1u);      // round to nearest even on the upper 16 bits
+  return u & 0xffff0000u;
+}
+__device__ __forceinline__ void mma_3x(float (&c)[4], float a0, float a1, float a2, float a3, uint32_t bh0, uint32_t bh1,
+                                       uint32_t bl0, uint32_t bl1) {
+  (void)bl0; (void)bl1;
+  mma_tf32(c, bf16_round(a0), bf16_round(a1), bf16_round(a2), bf16_round(a3),
+           bf16_round(__uint_as_float(bh0)), bf16_round(__uint_as_float(bh1)));
+}
+#else
 __device__ __forceinline__ void mma_3x(float (&c)[4], float a0, float a1, float a2, float a3, uint32_t bh0, uint32_t bh1,
                                        uint32_t bl0, uint32_t bl1) {
   uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
@@ -545,6 +562,7 @@ __device__ __forceinline__ void mma_3x(float (&c)[4], float a0, float a1, float 
   mma_tf32(c, h0, h1, h2, h3, bl0, bl1);
   mma_tf32(c, h0, h1, h2, h3, bh0, bh1);
 }
+#endif
 
 // EPQ phase on the tensor cores: [n x 16] . WT[16 x 32], 16 nodes per warp-task.  The K dimension is permuted so
 // that each lane's A operands are ONE 128-bit row segment (lane (g, t) holds h[row][4t..4t+3]): k-tile "A" uses
