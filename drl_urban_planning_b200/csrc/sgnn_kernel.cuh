@@ -1954,31 +1954,33 @@ __device__ void fused_tail(const StepArgs& a, float* smem, unsigned stage_bits) 
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(mybits) : "l"(a.gridbar + 2 + par) : "memory");
   const unsigned flagword = (a.seq << 2) | (mybits & 3u);
 
-  // ---- PUSH: local column sums of the owned slices -> every rank's buffer
+  // ---- PUSH: local column sums of the owned slices -> every rank's buffer.  Coalesced: a warp reads 32 consecutive
+  // columns of ONE partial row per load (one 128-byte line; four-row gathers cost four L1 wavefronts each); warp w owns
+  // column group w & 3 and the rows r = (w >> 2) mod 4; the four row groups are combined through shared memory in the
+  // order ((g0 + g1) + (g2 + g3)).
+  float* sPart = smem + 4096;                        // [4 row groups][SLICE] (the chain CTA's prefetch sits below 4096)
   for (int sl = blockIdx.x; sl < NSLICE; sl += gridDim.x) {
-    const int col = sl * SLICE + (tid >> 2);
-    float s;
-    {       // rows part, part+4, ...: eight loads in flight per thread, fixed summation order
-      const float* src = a.gpart + col;
-      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, s4 = 0.f, s5 = 0.f, s6 = 0.f, s7 = 0.f;
-      int r = part;
-      for (; r + 28 < nparts; r += 32) {
-        s0 += __ldcg(src + (size_t)r * G_ROW);        s1 += __ldcg(src + (size_t)(r + 4) * G_ROW);
-        s2 += __ldcg(src + (size_t)(r + 8) * G_ROW);  s3 += __ldcg(src + (size_t)(r + 12) * G_ROW);
-        s4 += __ldcg(src + (size_t)(r + 16) * G_ROW); s5 += __ldcg(src + (size_t)(r + 20) * G_ROW);
-        s6 += __ldcg(src + (size_t)(r + 24) * G_ROW); s7 += __ldcg(src + (size_t)(r + 28) * G_ROW);
-      }
-      if (r < nparts) {     // the last (up to seven) rows of this thread: one more batch of loads in flight together
-        float t[7];
+    const int lane = tid & 31, warp = tid >> 5, cg = warp & 3, rg = warp >> 2;
+    const float* src = a.gpart + sl * SLICE + cg * 32 + lane;
+    float s = 0.f;
+    for (int r0 = rg; r0 < nparts; r0 += 160) {      // all loads of a chunk of 160 rows in flight together, fixed order
+      float t[40];
 #pragma unroll
-        for (int j = 0; j < 7; ++j) t[j] = r + 4 * j < nparts ? __ldcg(src + (size_t)(r + 4 * j) * G_ROW) : 0.f;
-        s0 += t[0]; s1 += t[1]; s2 += t[2]; s3 += t[3]; s4 += t[4]; s5 += t[5]; s6 += t[6];
-      }
-      s = ((s0 + s1) + (s2 + s3)) + ((s4 + s5) + (s6 + s7));
+      for (int j = 0; j < 40; ++j) t[j] = r0 + 4 * j < nparts ? __ldcg(src + (size_t)(r0 + 4 * j) * G_ROW) : 0.f;
+#pragma unroll
+      for (int w = 1; w < 40; w <<= 1)
+#pragma unroll
+        for (int j = 0; j + w < 40; j += 2 * w) t[j] += t[j + w];
+      s += t[0];
     }
-    s += __shfl_xor_sync(0xffffffffu, s, 1);
-    s += __shfl_xor_sync(0xffffffffu, s, 2);         // all four lanes of the column hold the sum
-    for (int r = part; r < world; r += 4) st_relaxed(sh_push[r] + col, s, sys);     // lane p serves ranks p, p+4, ...
+    __syncthreads();                                 // the previous slice's partials have been consumed
+    sPart[rg * SLICE + cg * 32 + lane] = s;
+    __syncthreads();
+    if (tid < SLICE) {
+      const float v = (sPart[tid] + sPart[SLICE + tid]) + (sPart[2 * SLICE + tid] + sPart[3 * SLICE + tid]);
+      const int col = sl * SLICE + tid;
+      for (int r = 0; r < world; ++r) st_relaxed(sh_push[r] + col, v, sys);
+    }
   }
   __syncthreads();                                   // this CTA's pushes are issued (ordered before the releases below)
   {
@@ -2125,6 +2127,11 @@ __global__ void __launch_bounds__(NT, 1) k_sgnn(const __grid_constant__ StepArgs
   extern __shared__ __align__(16) float smem[];
   __shared__ __align__(8) uint64_t s_mbar[3];   // bulk-copy completion: [0] graph staging, [1] EPQ reload, [2] feature reload
   const long long t_cta0 = a.stamps ? clock64() : 0;
+  if (a.stamps && threadIdx.x == 0 && blockIdx.x == 0) {      // clock64 vs globaltimer (ns): the SM clock actually running
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    a.stamps[30] = t_cta0; a.stamps[32] = (long long)gt;
+  }
   if (threadIdx.x == 0) {
     mbar_init(s_mbar + 0, 1); mbar_init(s_mbar + 1, 1); mbar_init(s_mbar + 2, 1);
     fence_mbar_init();
@@ -2177,6 +2184,11 @@ __global__ void __launch_bounds__(NT, 1) k_sgnn(const __grid_constant__ StepArgs
     __syncthreads();
   }
   if (a.stamps && threadIdx.x == 0 && blockIdx.x < 160) a.stamps[64 + blockIdx.x] = clock64() - t_cta0;           // CTA busy time
+  if (a.stamps && threadIdx.x == 0 && blockIdx.x == 0) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    a.stamps[31] = clock64(); a.stamps[33] = (long long)gt;
+  }
   if constexpr (TRAIN) {
     if (a.fuse_tail) fused_tail(a, smem, stage_bits);
   }

@@ -8,3 +8,4 @@ python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.
 python bench.py --steps 50 --warmup 5 --skip-cpu --iter-states 0 > gpurun_out/r2c_bench_1gpu.json 2> gpurun_out/r2c_bench_1gpu.err; echo "1gpu rc=$?"
 for f in r2c_bench_1gpu r2c_bench_2gpu r2c_bench_2gpu_strong r2c_bench_2gpu_nccl; do python -c "
 import json; d=json.load(open('gpurun_out/$f.json')); print('$f', round(d['value']), d['ms_per_step'], d['roofline']['kernel_ms'], d.get('multi_gpu_selfcheck'))"; done
+python tools/tail_times.py 2>&1 | tail -5

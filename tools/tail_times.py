@@ -25,3 +25,13 @@ print("CTA0: wait at the grid barrier %d | slice sums + push + flags %d | flag w
       % (st[41] - st[40], st[42] - st[41], st[43] - st[42]))
 busy = st[64:64 + eng.grid]
 print("busy (graphs only) max %d mean %.0f" % (busy.max(), busy.mean()))
+dc, dg = st[31] - st[30], st[33] - st[32]
+print("CTA 0 graph loop: %d cycles in %d ns of globaltimer -> SM clock %.1f MHz" % (dc, dg, 1e3 * dc / max(dg, 1)))
+# whole-step time by CUDA events for comparison
+ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+eng.set_stamp_buffer(None)
+for _ in range(5): eng.ppo_step(*args, ids=ids)
+torch.cuda.synchronize(); ev0.record()
+for _ in range(50): eng.ppo_step(*args, ids=ids)
+ev1.record(); torch.cuda.synchronize()
+print("events: %.2f us per step (same minibatch, L2-resident)" % (ev0.elapsed_time(ev1) * 1e3 / 50))
