@@ -46,6 +46,9 @@ _PROTOS = {
                                  C.POINTER(C.c_int)]),
     "upb_pack_measure": (C.c_int, [C.c_int, _VP, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint64)]),
     "upb_pack_fill": (C.c_int, [C.c_int, _VP, C.c_int, C.c_int, C.c_int, _VP, C.c_uint64]),
+    "upb_pack_plan_create": (C.c_int, [C.c_int, _VP, C.c_int, C.c_int, C.c_int, C.POINTER(_VP), C.POINTER(C.c_uint64)]),
+    "upb_pack_plan_fill": (C.c_int, [_VP, _VP, C.c_int, C.c_int, C.c_int, _VP, C.c_uint64, _VP]),
+    "upb_pack_plan_destroy": (None, [_VP]),
     "upb_blob_info": (C.c_int, [_VP, C.c_uint64, C.POINTER(C.c_int), _VP]),
     "upb_create": (C.c_int, [C.POINTER(Config), C.POINTER(_VP)]),
     "upb_destroy": (None, [_VP]),

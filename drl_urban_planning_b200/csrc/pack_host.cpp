@@ -538,6 +538,83 @@ extern "C" int upb_pack_fill(int count, const void* const* state_arrays, int n_c
   return UPB_OK;
 }
 
+// ---- chunked packing: plan once, fill state ranges one after the other, so the caller can upload the byte ranges of a
+// finished chunk (host -> device copies run asynchronously) while the next chunk is being packed
+struct upb_pack_plan {
+  Plan plan;
+  int count = 0;
+};
+
+extern "C" int upb_pack_plan_create(int count, const void* const* state_arrays, int n_cap, int e_cap, int threads,
+                                    upb_pack_plan** plan_out, uint64_t* blob_bytes) {
+  if (!plan_out || !blob_bytes) return set_error(UPB_ERR_ARG, "pack_plan_create: null output");
+  upb_pack_plan* p = new (std::nothrow) upb_pack_plan();
+  if (!p) return set_error(UPB_ERR_ARG, "pack_plan_create: out of memory");
+  int rc = make_plan(count, state_arrays, n_cap, e_cap, threads, false, &p->plan);
+  if (rc != UPB_OK) { delete p; return rc; }
+  p->count = count;
+  *plan_out = p;
+  *blob_bytes = p->plan.hdr.total_bytes;
+  return UPB_OK;
+}
+
+extern "C" void upb_pack_plan_destroy(upb_pack_plan* p) { delete p; }
+
+extern "C" int upb_pack_plan_fill(upb_pack_plan* p, const void* const* state_arrays, int first, int count, int threads,
+                                  void* blob_host, uint64_t blob_bytes, uint64_t* ranges) {
+  if (!p || !blob_host || ((uintptr_t)blob_host & 15) || !ranges)
+    return set_error(UPB_ERR_ARG, "pack_plan_fill: bad argument (blob must be 16-byte aligned)");
+  const Plan& plan = p->plan;
+  if (first < 0 || count < 0 || first + count > p->count) return set_error(UPB_ERR_ARG, "pack_plan_fill: range outside the plan");
+  if (blob_bytes < plan.hdr.total_bytes) return set_error(UPB_ERR_CAPACITY, "pack_plan_fill: blob buffer too small");
+  uint8_t* blob = (uint8_t*)blob_host;
+  const BlobHeader& h = plan.hdr;
+  int nr = 0;
+  auto add = [&](uint64_t off, uint64_t len) { ranges[2 * nr] = off; ranges[2 * nr + 1] = len; ++nr; };
+  if (first == 0) {      // header + descriptor table travel with the first chunk
+    memcpy(blob, &h, sizeof(BlobHeader));
+    if (p->count > 0) memcpy(blob + h.off_desc, plan.desc.data(), sizeof(GraphDesc) * (size_t)p->count);
+    add(0, h.off_x);
+  } else {
+    add(0, 0);
+  }
+  std::atomic<int> bad{p->count};
+  std::atomic<const char*> why{nullptr};
+  parallel_for(count, threads, [&](int j) {
+    const int i = first + j;
+    const char* err = fill_one(view(state_arrays, i), plan.desc[i], h, blob, i);
+    if (err) {
+      int cur = bad.load();
+      while (i < cur && !bad.compare_exchange_weak(cur, i)) {}
+      why.store(err);
+    }
+  });
+  if (bad.load() < p->count) {
+    char buf[256];
+    snprintf(buf, sizeof(buf), "pack: state %d: %s", bad.load(), why.load());
+    return set_error(UPB_ERR_FORMAT, buf);
+  }
+  // byte ranges of the eight per-graph sections written by this chunk (section start of state `first` .. of state `last`)
+  const int last = first + count;
+  const bool end = last >= p->count;
+  const GraphDesc* d = plan.desc.data();
+  auto span = [&](uint64_t base, uint64_t next_base, uint64_t unit, int64_t a, int64_t b_or_neg) {
+    const uint64_t lo = base + unit * (uint64_t)a;
+    const uint64_t hi = b_or_neg < 0 ? next_base : base + unit * (uint64_t)b_or_neg;
+    add(lo, hi > lo ? hi - lo : 0);
+  };
+  if (count == 0) { for (int k = 0; k < 8; ++k) add(0, 0); return UPB_OK; }
+  span(h.off_x, h.off_num, kNodeStride * sizeof(float), d[first].x_row, end ? -1 : d[last].x_row);
+  span(h.off_num, h.off_cur, kNumDim * sizeof(float), first, end ? -1 : last);
+  span(h.off_cur, h.off_rowptr, kNodeStride * sizeof(float), first, end ? -1 : last);
+  span(h.off_rowptr, h.off_order, sizeof(uint16_t), d[first].rp_off, end ? -1 : d[last].rp_off);
+  span(h.off_order, h.off_adj, sizeof(uint16_t), d[first].ord_off, end ? -1 : d[last].ord_off);
+  span(h.off_adj, h.off_cand_uv, sizeof(uint32_t), d[first].adj_off, end ? -1 : d[last].adj_off);
+  span(h.off_cand_uv, h.off_cand_idx, sizeof(uint32_t), d[first].cand_off, end ? -1 : d[last].cand_off);
+  span(h.off_cand_idx, h.total_bytes, sizeof(int32_t), d[first].cand_off, end ? -1 : d[last].cand_off);
+  return UPB_OK;
+}
+
 extern "C" int upb_blob_info(const void* blob_host, uint64_t blob_bytes, int* count, int32_t* per_graph4) {
   if (!blob_host || blob_bytes < sizeof(BlobHeader)) return set_error(UPB_ERR_ARG, "blob_info: bad blob");
   const BlobHeader* h = (const BlobHeader*)blob_host;

@@ -153,3 +153,40 @@ def pack_states(states: Sequence[Sequence], n_cap: Optional[int] = None, e_cap: 
                "upb_pack_fill")
     del keep
     return blob
+
+
+def pack_and_upload(states: Sequence[Sequence], n_cap: int, e_cap: int, device, threads: int = 0, chunk: int = 2048,
+                    host=None, dev=None) -> PackedGraphs:
+    """Pack a large buffer of states and upload it, overlapped: the blob is filled chunk by chunk (`chunk` states at a
+    time, all packer threads on one chunk) and the byte ranges of every finished chunk are copied to the device with
+    asynchronous copies from the pinned buffer while the next chunk is being packed.  `host` / `dev` are reusable pinned /
+    device uint8 tensors (grown when too small).  Result: the same blob as pack_states(...).to(device)."""
+    import torch
+    if len(states) == 0:
+        raise ValueError("pack_and_upload needs at least one state")
+    L = _lib.lib()
+    ptrs, keep = _pointer_table(states, n_cap, e_cap)
+    plan, nbytes = C.c_void_p(), C.c_uint64()
+    _lib.check(L.upb_pack_plan_create(len(states), ptrs.ctypes.data, n_cap, e_cap, threads, C.byref(plan),
+                                      C.byref(nbytes)), "upb_pack_plan_create")
+    try:
+        nb = int(nbytes.value)
+        if host is None or host.numel() < nb:
+            host = torch.empty(nb, dtype=torch.uint8, pin_memory=True)
+        if dev is None or dev.numel() < nb:
+            dev = torch.empty(nb, dtype=torch.uint8, device=device)
+        ranges = np.zeros((9, 2), np.uint64)
+        for first in range(0, len(states), chunk):
+            cnt = min(chunk, len(states) - first)
+            _lib.check(L.upb_pack_plan_fill(plan, ptrs.ctypes.data, first, cnt, threads, host.data_ptr(), nb,
+                                            ranges.ctypes.data), "upb_pack_plan_fill")
+            for off, ln in ranges:
+                off, ln = int(off), int(ln)
+                if ln:
+                    dev[off:off + ln].copy_(host[off:off + ln], non_blocking=True)
+    finally:
+        L.upb_pack_plan_destroy(plan)
+    del keep
+    blob = PackedGraphs(host, nb, len(states), n_cap, e_cap)
+    blob.dev = dev
+    return blob

@@ -28,7 +28,7 @@ import torch
 
 from . import _lib
 from .engine import Engine
-from .packing import PackedGraphs, pack_states, infer_caps
+from .packing import PackedGraphs, pack_and_upload, pack_states, infer_caps
 
 
 class PPOUpdater:
@@ -88,13 +88,11 @@ class PPOUpdater:
     def load_states(self, states: Sequence, actions, exps=None):
         """Pack + upload the iteration's rollout states (list of reference 9-array states) and their actions."""
         nvtx = torch.cuda.nvtx
-        nvtx.range_push("upb.pack_states")
-        self.blob = pack_states(states, self.engine.n_cap, self.engine.e_cap, threads=self.pack_threads,
-                                out_host=getattr(self, "_host_blob_buf", None))
-        self._host_blob_buf = self.blob.host if hasattr(self.blob.host, "data_ptr") else None
-        nvtx.range_pop()
-        nvtx.range_push("upb.upload_blob")
-        self.blob.to(self.device, out=self._dev_blob_buf)
+        nvtx.range_push("upb.pack_and_upload")
+        # chunked: the H2D copies of a packed chunk run while the next chunk is being packed
+        self.blob = pack_and_upload(states, self.engine.n_cap, self.engine.e_cap, self.device, threads=self.pack_threads,
+                                    host=getattr(self, "_host_blob_buf", None), dev=self._dev_blob_buf)
+        self._host_blob_buf = self.blob.host
         nvtx.range_pop()
         self._dev_blob_buf = self.blob.dev
         T = self.blob.count

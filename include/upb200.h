@@ -97,6 +97,18 @@ int upb_pack_measure(int count, const void* const* state_arrays, int n_cap, int 
                      uint64_t* blob_bytes);
 int upb_pack_fill(int count, const void* const* state_arrays, int n_cap, int e_cap, int threads,
                   void* blob_host, uint64_t blob_bytes);
+/* Chunked packing for large buffers (a whole iteration's rollout states, ~1 GB): plan once, then fill the states
+ * [first, first + count) chunk by chunk.  Every fill returns the byte ranges of the blob it has completed -- ranges[9][2]
+ * = {offset, length}: [0] header + descriptor table (first chunk only), [1..8] the x, numerical, current-node, rowptr,
+ * order, adj, cand_uv, cand_idx sections -- so the caller can start the host -> device copies of a chunk while the next
+ * chunk is being packed (PackedGraphs.pack_and_upload).  The result equals upb_pack_fill's byte for byte. */
+typedef struct upb_pack_plan upb_pack_plan;
+int upb_pack_plan_create(int count, const void* const* state_arrays, int n_cap, int e_cap, int threads,
+                         upb_pack_plan** plan_out, uint64_t* blob_bytes);
+int upb_pack_plan_fill(upb_pack_plan* plan, const void* const* state_arrays, int first, int count, int threads,
+                       void* blob_host, uint64_t blob_bytes, uint64_t* ranges);
+void upb_pack_plan_destroy(upb_pack_plan* plan);
+
 /* per-graph (n, e, k, stage) of a packed host blob, 4 ints per graph (for tests and load balancing) */
 int upb_blob_info(const void* blob_host, uint64_t blob_bytes, int* count, int32_t* per_graph4);
 

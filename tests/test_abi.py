@@ -55,3 +55,12 @@ def test_cpulist_parser_of_the_numa_helper():
     import torch
     if not torch.cuda.is_available():
         assert bind_host_to_gpu_node(0) is None      # no GPU topology to read: nothing is changed
+
+
+def test_mlp_header_constants_match_python():
+    hdr = open(os.path.join(ROOT, "include", "upb200.h")).read()
+    consts = dict(re.findall(r"#define\s+(UPB_[A-Z_]+)\s+(\d+)", hdr))
+    assert int(consts["UPB_MLP_NUM_PARAMS"]) == _lib.UPB_MLP_NUM_PARAMS == PL.MLP.num_params
+    assert int(consts["UPB_MLP_GRAD_STRIDE"]) == _lib.UPB_MLP_GRAD_STRIDE
+    assert int(consts["UPB_MLP_STAT_OFFSET"]) == _lib.UPB_MLP_STAT_OFFSET
+    assert _lib.UPB_MLP_STAT_OFFSET + _lib.UPB_STAT_COUNT == _lib.UPB_MLP_GRAD_STRIDE

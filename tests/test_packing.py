@@ -166,3 +166,33 @@ def test_pack_from_concurrent_threads_and_after_fork():
             os._exit(ok)
     _, status = os.waitpid(pid, 0)
     assert os.WEXITSTATUS(status) == 0
+
+
+def test_chunked_plan_fill_equals_one_shot_and_ranges_cover_the_blob():
+    """upb_pack_plan_create / _fill (chunked packing for the overlapped upload of PackedGraphs.pack_and_upload): the blob
+    is byte-identical to upb_pack_fill's and the byte ranges reported per chunk tile it exactly once."""
+    import ctypes as C
+    from drl_urban_planning_b200.packing import _pointer_table
+    states, _ = synth.make_states(5, "small", 57)
+    ref = pack_states(states, pinned=False)
+    refb = np.asarray(ref.host)[:ref.nbytes] if not hasattr(ref.host, "numpy") else ref.host.numpy()[:ref.nbytes]
+    L = _lib.lib()
+    ptrs, keep = _pointer_table(states, ref.n_cap, ref.e_cap)
+    plan, nb = C.c_void_p(), C.c_uint64()
+    _lib.check(L.upb_pack_plan_create(len(states), ptrs.ctypes.data, ref.n_cap, ref.e_cap, 2, C.byref(plan), C.byref(nb)))
+    assert nb.value == ref.nbytes
+    raw = np.zeros(nb.value + 16, np.uint8)
+    off = (-raw.ctypes.data) % 16
+    host = raw[off:off + nb.value]
+    covered = np.zeros(nb.value, np.int32)
+    ranges = np.zeros((9, 2), np.uint64)
+    for first in range(0, len(states), 10):
+        cnt = min(10, len(states) - first)
+        _lib.check(L.upb_pack_plan_fill(plan, ptrs.ctypes.data, first, cnt, 2, host.ctypes.data, nb.value,
+                                        ranges.ctypes.data))
+        for o, ln in ranges:
+            covered[int(o):int(o) + int(ln)] += 1
+    assert L.upb_pack_plan_fill(plan, ptrs.ctypes.data, 50, 10, 2, host.ctypes.data, nb.value, ranges.ctypes.data) != 0
+    L.upb_pack_plan_destroy(plan)
+    assert np.array_equal(host, refb)
+    assert (covered == 1).all()
