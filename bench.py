@@ -518,8 +518,10 @@ def main():
         iteration = {"states": T, "epochs": 4, "mini_batch_size": 256, "optimiser_steps": nsteps, "seconds": secs[1],
                      "first_call_seconds": secs[0], "graph_samples_per_s": nsteps * 256 / secs[1],
                      "h2d_bytes": int(up.blob.nbytes), "total_loss": float(res["total_loss"]),
-                     "path": "reference-layout host lists -> upb_pack_fill (once) -> pinned -> one H2D -> upb_forward sweep -> "
-                             "upb_gae -> 4 x floor(T/256) upb_ppo_step -> loss statistics read back once per epoch"}
+                     "path": "reference-layout host lists -> upb_pack_plan_fill chunk by chunk into pinned memory, each chunk's "
+                             "H2D copies overlapping the next chunk's packing -> upb_forward sweep -> upb_gae -> "
+                             "4 x floor(T/256) upb_ppo_step (next epoch's host work overlapped) -> loss statistics read back "
+                             "once per epoch"}
         del up, it_states
         torch.cuda.empty_cache()
 
