@@ -1119,10 +1119,12 @@ __device__ __forceinline__ void softmax_seeds(const StepArgs& a, const BlobHeade
   if (k > 0) {
     greedy = g.cidx[lbest];
     if (a.actions) logp = slot >= 0 ? g.z[slot] - lse : MASK_FILL - lse;
-  } else {      // every logit equals the fill value: uniform over the padded width
-    const float cap = (float)(g.stage == 0 ? hd.e_cap : hd.n_cap);
-    H = logf(cap);
-    if (a.actions) logp = -logf(cap);
+  } else {      // every logit equals the fill value -2^32+1.  The distribution is uniform over the padded width, but the
+                // reference's fp32 log-softmax returns 0 for every entry (logsumexp = fill + log(width) rounds back to
+                // fill, ulp 512): log_prob = 0, entropy = 0 -- measured on the unmodified reference
+                // (tests/golden/edge_empty.npz) and reproduced here
+    H = 0.f;
+    logp = 0.f;
   }
   const float V = sc[SC_VALUE];
   if (lane == 0) {

@@ -123,7 +123,10 @@ def forward(P: Dict[str, np.ndarray], g: Graph, action: Optional[int] = None, ke
     if stage_id >= 0:
         if idx.size == 0:
             # every logit equals the fill value -> uniform over the padded width (policy.py:50-52)
-            out.update(log_prob=-np.log(cap), entropy=np.log(cap), greedy=0)
+            # every logit equals the fill value -2^32+1: in the reference's fp32 arithmetic logsumexp(logits) = fill
+            # + log(cap) rounds back to fill (ulp 512), so the normalised logits are exactly 0: log_prob = 0, entropy = 0
+            # (measured on the unmodified reference, tests/golden/edge_empty.npz), arg-max = first index
+            out.update(log_prob=0.0, entropy=0.0, greedy=0)
             p = logp = np.zeros(0)
         else:
             zs = z - z.max()

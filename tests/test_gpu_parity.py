@@ -415,3 +415,18 @@ def test_select_action_greedy_and_sampled(dev):
     ids = torch.as_tensor(np.array([5, 7, 11], np.int32), device=dev)
     part = eng.select_action(blob, params, uniforms=t(u, dev), ids=ids).cpu().numpy()
     assert np.array_equal(part[[5, 7, 11]], picked[[5, 7, 11]]) and part[[0, 1, 2]].tolist() == [0, 0, 0]
+
+
+def test_empty_action_masks_match_reference(golden_dir, dev):
+    """The reference's fp32 behaviour on an all-masked state (log_prob = 0, entropy = 0, arg-max = 0), both stages, for
+    the SGNN kernel; the rl-mlp kernel shares the code path (tests/test_mlp.py)."""
+    z = np.load(os.path.join(golden_dir, "edge_empty.npz"))
+    states = expand_states(z)
+    blob = pack_states(states).to(dev)
+    eng = make_engine(dev, blob.n_cap, blob.e_cap)
+    value, logp, ent, greedy = eng.forward(blob, t(z["params"], dev), t(z["actions"], dev), want_greedy=True)
+    assert rel(value.cpu().numpy(), z["values"].ravel()) < TOL
+    assert np.allclose(logp.cpu().numpy(), z["log_probs"].ravel(), rtol=1e-4, atol=1e-7)
+    assert np.allclose(ent.cpu().numpy(), z["entropies"].ravel(), rtol=1e-4, atol=1e-7)
+    stage = z["stage"][:, :2].argmax(1)
+    assert np.array_equal(greedy.cpu().numpy(), z["greedy"][np.arange(3), stage].astype(np.int64))

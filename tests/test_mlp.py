@@ -156,3 +156,48 @@ def test_mlp_update_params_runs_on_the_updater():
             agent.step(MP.stack_states([states[j] for j in idx]), act[idx], adv[idx], ret[idx], fixed[idx],
                        torch.arange(B))
     assert rel(up.flat_params(), agent.flat()) < 2e-5
+
+
+@pytest.mark.gpu
+def test_mlp_large_graphs_and_edge_cases_match_oracle_port():
+    """k_mlp beyond its shared-memory budget (n > 464 or 2e > 5632: the global-scratch path), both stages, an empty
+    action mask and exps = 0 rows, against the oracle port (autograd) on the same padded states."""
+    from drl_urban_planning_b200.engine import Engine
+    from drl_urban_planning_b200.packing import pack_states
+    dev = torch.device("cuda", 0)
+    t = lambda x: torch.as_tensor(np.ascontiguousarray(x), device=dev)
+    sizes = [600, 40, 900, 470, 300, 12]
+    stages = [0, 1, 0, 1, 0, 0]
+    states, actions = synth.make_states(13, "hlg", len(sizes), sizes=sizes, stages=stages)
+    states[5][6][:] = False                                   # empty land-use mask: uniform over the padded width
+    count = len(states)
+    adv, ret, exps = synth.make_ppo_targets(13, count)
+    exps[1] = 0.0
+    fixed = np.full((count, 1), -3.3, np.float32)
+    flat = L.default_init(13)
+    blob = pack_states(states).to(dev)
+    assert (blob.info[:, 0] > 464).sum() >= 2
+    eng = Engine(dev, blob.n_cap, blob.e_cap, model="mlp")
+    params = t(flat)
+    value, logp, ent, greedy = eng.forward(blob, params, t(actions), want_greedy=True)
+    n_ind = int((exps != 0).sum())
+    grad = eng.ppo_grad(blob, params, t(actions), t(adv), t(ret), t(fixed), t(exps), 1.0 / count, 1.0 / n_ind)
+    torch.cuda.synchronize()
+    agent = MP.MLPPortAgent(flat)
+    b = MP.stack_states(states)
+    act = torch.tensor(actions)
+    ind = torch.tensor(exps).nonzero(as_tuple=False).squeeze(1)
+    with torch.no_grad():
+        v_ref = MP.value(agent.P, b).numpy().ravel()
+        lp_ref, en_ref = MP.log_prob_entropy(agent.P, b, act)
+        gr_ref = MP.greedy_action(agent.P, b).numpy()
+    losses = agent.backward(b, act, torch.tensor(adv), torch.tensor(ret), torch.tensor(fixed), ind)
+    assert rel(value.cpu().numpy(), v_ref) < 1e-4
+    assert rel(logp.cpu().numpy(), lp_ref.numpy().ravel()) < 1e-4
+    assert rel(ent.cpu().numpy(), en_ref.numpy().ravel()) < 1e-4
+    st = np.array(stages)
+    keep = np.arange(count) != 5                              # the empty mask has no defined arg-max
+    assert np.array_equal(greedy.cpu().numpy()[keep], gr_ref[np.arange(count), st][keep].astype(np.int64))
+    assert np.allclose(eng.read_losses(grad), losses, rtol=1e-4, atol=1e-5)
+    worst, where = per_tensor_rel(grad.cpu().numpy()[:L.num_params], agent.flat_grad())
+    assert worst < 1e-4, (worst, where)

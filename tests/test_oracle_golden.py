@@ -170,3 +170,20 @@ def test_torch_port_update_policy_matches_reference(golden_dir):
             losses.append(agent.step(b, act[idx], adv[idx], ret[idx], fixed[idx], ind))
     assert np.allclose(np.array(losses), z["losses"], rtol=2e-5, atol=2e-6)
     assert rel(agent.flat(), z["params_after"]) < 5e-6
+
+
+def test_empty_action_masks_match_reference(golden_dir):
+    """All logits equal to the fill value: the reference's fp32 log-softmax yields log_prob = 0 and entropy = 0 (not the
+    -log(width) / log(width) of exact arithmetic), arg-max = first index."""
+    z = np.load(os.path.join(golden_dir, "edge_empty.npz"))
+    states = expand_states(z)
+    assert z["log_probs"].ravel()[1] == 0.0 and z["log_probs"].ravel()[2] == 0.0
+    assert abs(z["entropies"].ravel()[1]) == 0.0 and abs(z["entropies"].ravel()[2]) == 0.0
+    r = ON.ppo_minibatch(z["params"], states, z["actions"], np.zeros((3, 1), np.float32), np.zeros((3, 1), np.float32),
+                         np.zeros((3, 1), np.float32), np.ones(3, np.float32), want_grad=False)
+    assert np.allclose(r["log_prob"], z["log_probs"].ravel(), rtol=2e-5, atol=1e-7)
+    assert np.allclose(r["entropy"], z["entropies"].ravel(), rtol=2e-5, atol=1e-7)
+    b = TP.stack_states(states)
+    with torch.no_grad():
+        lp, ent = TP.log_prob_entropy(TP.params_from_flat(torch.tensor(z["params"])), b, torch.tensor(z["actions"]))
+    assert np.allclose(lp.numpy(), z["log_probs"], rtol=2e-6, atol=1e-7) and np.allclose(ent.numpy(), z["entropies"], atol=1e-6)
