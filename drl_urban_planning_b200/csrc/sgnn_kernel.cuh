@@ -1692,11 +1692,11 @@ __device__ void graph_body(const StepArgs& a, const BlobHeader& hd, const GraphD
     if (warp < KW) {   // g_W[o][c] = sum_i GPQ[i][o] h^l[i][c]: 4x4 register tiles, K split over KW warps
       float* redbuf = smem + S_EPQ;              // [KW][512]
       const int to = lane >> 2, tc = lane & 3;
-      float acc[4][4];
+      // packed FMAs: accp[c][xp] = (acc[2 xp][c], acc[2 xp + 1][c]); the GPQ float4 supplies the pairs (x, y), (z, w)
+      // as they sit in registers, the h components are duplicated into both halves (FFMA2: two FMAs per issue)
+      float2 accp[4][2];
 #pragma unroll
-      for (int x = 0; x < 4; ++x)
-#pragma unroll
-        for (int y = 0; y < 4; ++y) acc[x][y] = 0.f;
+      for (int c = 0; c < 4; ++c) { accp[c][0] = make_float2(0.f, 0.f); accp[c][1] = make_float2(0.f, 0.f); }
       for (int i = warp; i < n; i += 8 * KW) {   // eight nodes per trip: their global h rows are in flight together
         float4 gq[8], hv[8];
 #pragma unroll
@@ -1710,17 +1710,24 @@ __device__ void graph_body(const StepArgs& a, const BlobHeader& hd, const GraphD
           gq[u] = ii < n ? ld4(g.GPQ + ii * 32 + to * 4) : f4(0.f);
         }
 #pragma unroll
-        for (int u = 0; u < 8; ++u)
+        for (int u = 0; u < 8; ++u) {
+          const float2 g01 = make_float2(gq[u].x, gq[u].y), g23 = make_float2(gq[u].z, gq[u].w);
 #pragma unroll
-          for (int x = 0; x < 4; ++x) {
-            const float gx = comp(gq[u], x);
-            acc[x][0] = fmaf(gx, hv[u].x, acc[x][0]); acc[x][1] = fmaf(gx, hv[u].y, acc[x][1]);
-            acc[x][2] = fmaf(gx, hv[u].z, acc[x][2]); acc[x][3] = fmaf(gx, hv[u].w, acc[x][3]);
+          for (int c = 0; c < 4; ++c) {
+            const float hc_ = comp(hv[u], c);
+            const float2 h2 = make_float2(hc_, hc_);
+            accp[c][0] = __ffma2_rn(g01, h2, accp[c][0]);
+            accp[c][1] = __ffma2_rn(g23, h2, accp[c][1]);
           }
+        }
       }
 #pragma unroll
-      for (int x = 0; x < 4; ++x)
-        st4(redbuf + warp * 512 + (to * 4 + x) * 16 + tc * 4, make_float4(acc[x][0], acc[x][1], acc[x][2], acc[x][3]));
+      for (int x = 0; x < 4; ++x) {
+        const int xp = x >> 1;
+        st4(redbuf + warp * 512 + (to * 4 + x) * 16 + tc * 4,
+            (x & 1) ? make_float4(accp[0][xp].y, accp[1][xp].y, accp[2][xp].y, accp[3][xp].y)
+                    : make_float4(accp[0][xp].x, accp[1][xp].x, accp[2][xp].x, accp[3][xp].x));
+      }
     }
     gh_phase_tc(g, Wpq, l == 1);     // g_h = g_h' + GPQ Wpq (residual), in place
     __syncthreads();
@@ -1753,11 +1760,9 @@ __device__ void graph_body(const StepArgs& a, const BlobHeader& hd, const GraphD
     for (int task = tid; task < n * 4; task += NT) hs = hs + ld4(g.H + (task >> 2) * 16 + q * 4);
     if constexpr (!BIG) { mbar_wait(mbar + 2, mpar); __syncthreads(); }
     const int tcc = lane / 6, tf = lane % 6;     // 4 channel tiles x 6 feature tiles (lanes 24..31 idle)
-    float acc[4][4];
+    float2 accp[4][2];     // packed FMAs: accp[f][xp] = (acc[2 xp][f], acc[2 xp + 1][f]), see the g_W loop
 #pragma unroll
-    for (int x = 0; x < 4; ++x)
-#pragma unroll
-      for (int y = 0; y < 4; ++y) acc[x][y] = 0.f;
+    for (int f = 0; f < 4; ++f) { accp[f][0] = make_float2(0.f, 0.f); accp[f][1] = make_float2(0.f, 0.f); }
     if (lane < 24) {
       for (int i = warp; i < n; i += 4 * NW) {   // four nodes per trip
         float4 gh[4], xv[4];
@@ -1770,17 +1775,24 @@ __device__ void graph_body(const StepArgs& a, const BlobHeader& hd, const GraphD
           gh[u] = ok ? ld4(g.H + ii * 16 + tcc * 4) : f4(0.f);
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
+        for (int u = 0; u < 4; ++u) {
+          const float2 g01 = make_float2(gh[u].x, gh[u].y), g23 = make_float2(gh[u].z, gh[u].w);
 #pragma unroll
-          for (int x = 0; x < 4; ++x) {
-            const float gx = comp(gh[u], x);
-            acc[x][0] = fmaf(gx, xv[u].x, acc[x][0]); acc[x][1] = fmaf(gx, xv[u].y, acc[x][1]);
-            acc[x][2] = fmaf(gx, xv[u].z, acc[x][2]); acc[x][3] = fmaf(gx, xv[u].w, acc[x][3]);
+          for (int f = 0; f < 4; ++f) {
+            const float xf = comp(xv[u], f);
+            const float2 x2 = make_float2(xf, xf);
+            accp[f][0] = __ffma2_rn(g01, x2, accp[f][0]);
+            accp[f][1] = __ffma2_rn(g23, x2, accp[f][1]);
           }
+        }
       }
 #pragma unroll
-      for (int x = 0; x < 4; ++x)
-        st4(redbuf + warp * 384 + (tcc * 4 + x) * 24 + tf * 4, make_float4(acc[x][0], acc[x][1], acc[x][2], acc[x][3]));
+      for (int x = 0; x < 4; ++x) {
+        const int xp = x >> 1;
+        st4(redbuf + warp * 384 + (tcc * 4 + x) * 24 + tf * 4,
+            (x & 1) ? make_float4(accp[0][xp].y, accp[1][xp].y, accp[2][xp].y, accp[3][xp].y)
+                    : make_float4(accp[0][xp].x, accp[1][xp].x, accp[2][xp].x, accp[3][xp].x));
+      }
     }
     block_sum_q4(hs, sRed, sV + V_TMP16);        // barriers inside publish redbuf
     if (tid < 384) {
