@@ -171,6 +171,52 @@ def test_matches_numpy_oracle(community, count, seed, dev):
                        rtol=1e-4, atol=1e-5)
 
 
+def _reciprocal_tiers(flat, states):
+    """Per GCN layer, which form of the pull's tanh terms the kernel will pick over the batch (sgnn_kernel.cuh
+    fwd_term / bwd_term): 0 = one shared reciprocal per entry (|pre-activation| <= 10.9), 1 = the exact two."""
+    P = ON._p64(flat)
+    tiers = [set(), set()]
+    for st in states:
+        hs = ON.forward(P, ON.unpad(st), keep=True)["cache"]["hs"]
+        for l in range(2):
+            W, b = P[f"gcn{l}_w"], P[f"gcn{l}_b"]
+            amax = max(np.abs(hs[l] @ W[:, :16].T + b).max(), np.abs(hs[l] @ W[:, 16:].T).max())
+            assert amax < 38.0, "beyond the exp-form's clamp (|pre-activation| <= 40): not a case this test is for"
+            tiers[l].add(0 if amax <= 10.9 else 1)
+    return tiers
+
+
+@pytest.mark.parametrize("scale,want", [(10.0, {0}), (20.0, {0, 1}), (30.0, {1})])
+def test_saturated_edge_activations_match_numpy_oracle(scale, want, dev):
+    """The pulls compute both tanh terms of an entry from ONE reciprocal while the product of their denominators
+    cannot overflow, and from two otherwise; the form is picked per graph and layer from the measured
+    |pre-activation|.  Edge-MLP weights scaled up walk a batch through both forms (checked from the oracle's own
+    activations), up to near the exp-form's clamp, and values / log-probs / entropies / gradients stay within the
+    fp32 bar of the float64 oracle."""
+    count, seed = 24, 5
+    states, actions = synth.make_states(seed, "small", count)
+    adv, ret, exps = synth.make_ppo_targets(seed, count)
+    flat = PL.default_init(seed).copy()
+    for name in ("gcn0_w", "gcn1_w"):
+        sl = PL.SLOTS[name]
+        flat[sl.offset:sl.offset + sl.size] *= scale
+    tiers = _reciprocal_tiers(flat, states)
+    assert want <= (tiers[0] | tiers[1]), tiers
+    fixed = np.random.default_rng(seed).normal(-3.0, 0.3, size=(count, 1)).astype(np.float32)
+    ref = ON.ppo_minibatch(flat, states, actions, adv, ret, fixed, exps)
+    blob = pack_states(states).to(dev)
+    eng = make_engine(dev, blob.n_cap, blob.e_cap)
+    params = t(flat, dev)
+    value, logp, ent = eng.forward(blob, params, t(actions, dev))
+    assert rel(value.cpu().numpy(), ref["value"]) < TOL
+    assert rel(logp.cpu().numpy(), ref["log_prob"]) < TOL
+    assert rel(ent.cpu().numpy(), ref["entropy"]) < TOL
+    grad = eng.ppo_grad(blob, params, t(actions, dev), t(adv, dev), t(ret, dev), t(fixed, dev), t(exps, dev),
+                        1.0 / count, 1.0 / int((exps != 0).sum()))
+    worst, where = per_tensor_rel(grad.cpu().numpy()[:PL.NUM_PARAMS], ref["grad"])
+    assert worst < TOL, (worst, where)
+
+
 def big_states(seed, count):
     """Graphs beyond the shared-memory fast path (n > 464 or 2e > 5632 or > 160 candidates), up to the caps."""
     spec = synth.CommunitySpec("big", 1000, 3000, 470, 1000, 3.0, 0.3)

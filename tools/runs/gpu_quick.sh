@@ -1,9 +1,8 @@
 #!/bin/bash
-# quick kernel check: parity tests of the SGNN path + bench line(s) + phase table
+# quick kernel check: parity tests of the SGNN path + bench line + phase table
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_update.py -m gpu -x -q 2>&1 | tail -2
-for pdl in 0 1 0 1; do
-UPB_PDL=$pdl timeout 300 python bench.py --steps 200 --warmup 10 --skip-cpu --skip-e2e --iter-states 0 > gpurun_out/quick_bench.json 2> gpurun_out/quick_bench.err; echo "pdl=$pdl bench rc=$?"
+timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_update.py -m gpu -x -q 2>&1 | tail -4
+timeout 300 python bench.py --steps 200 --warmup 10 --skip-cpu --skip-e2e --iter-states 0 > gpurun_out/quick_bench.json 2> gpurun_out/quick_bench.err; echo "bench rc=$?"
 python -c "
 import json; d=json.load(open('gpurun_out/quick_bench.json')); print(round(d['value']), d['ms_per_step'], d['roofline']['kernel_ms'], d['roofline']['frac'])"
-done
+python tools/phase_times.py 2>&1 | grep -E "cycles|total"
