@@ -126,6 +126,7 @@ constexpr int S_TOTAL = S_H + NS * 16;
 constexpr size_t SMEM_BYTES = (size_t)S_TOTAL * 4;
 static_assert(SMEM_BYTES <= 232448, "shared memory budget (227 KB)");
 constexpr int KW = 16;            // warps that share the K dimension of the g_W tile reduction
+constexpr int HIN_NODES = (NS * 32 - KW * 512) / 16;   // h rows that fit behind the g_W reduction buffer in the EPQ region
 static_assert(KW * 512 <= NS * 32 && NW * 384 <= NS * 32, "cross-warp reduction buffers alias the EPQ region");
 static_assert(NW == kPullWarps, "the packer lays the pull schedule out for NT / 32 warps");
 static_assert(NT >= 512 && KW <= NW, "thread (r, c) = (tid >> 4, tid & 15) mappings use the first 512 threads");
@@ -1194,6 +1195,52 @@ __device__ __forceinline__ void softmax_seeds(const StepArgs& a, const BlobHeade
   }
 }
 
+// partial g_W tile of one warp: redbuf[warp][o][c] = sum over this warp's nodes of GPQ[i][o] h[i][c]; 4x4 register
+// tiles (lane = 8 output groups x 4 channel groups), eight nodes per trip.  SMEM: h rows staged in shared memory,
+// else read from the global scratch (L2).
+// packed FMAs: accp[c][xp] = (acc[2 xp][c], acc[2 xp + 1][c]); the GPQ float4 supplies the pairs (x, y), (z, w) as they
+// sit in registers, the h components are duplicated into both halves (FFMA2: two FMAs per issue)
+template <bool SMEM>
+__device__ __forceinline__ void gw_partial(const GraphView& g, const float* hin, int n, float* redbuf) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int to = lane >> 2, tc = lane & 3;
+  float2 accp[4][2];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) { accp[c][0] = make_float2(0.f, 0.f); accp[c][1] = make_float2(0.f, 0.f); }
+  for (int i = warp; i < n; i += 8 * KW) {   // eight nodes per trip: their h rows are in flight together
+    float4 gq[8], hv[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int ii = i + u * KW;
+      if constexpr (SMEM) hv[u] = ii < n ? ld4(hin + ii * 16 + tc * 4) : f4(0.f);
+      else hv[u] = ii < n ? __ldcg(reinterpret_cast<const float4*>(hin + (size_t)ii * 16 + tc * 4)) : f4(0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int ii = i + u * KW;
+      gq[u] = ii < n ? ld4(g.GPQ + ii * 32 + to * 4) : f4(0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const float2 g01 = make_float2(gq[u].x, gq[u].y), g23 = make_float2(gq[u].z, gq[u].w);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float hc_ = comp(hv[u], c);
+        const float2 h2 = make_float2(hc_, hc_);
+        accp[c][0] = __ffma2_rn(g01, h2, accp[c][0]);
+        accp[c][1] = __ffma2_rn(g23, h2, accp[c][1]);
+      }
+    }
+  }
+#pragma unroll
+  for (int x = 0; x < 4; ++x) {
+    const int xp = x >> 1;
+    st4(redbuf + warp * 512 + (to * 4 + x) * 16 + tc * 4,
+        (x & 1) ? make_float4(accp[0][xp].y, accp[1][xp].y, accp[2][xp].y, accp[3][xp].y)
+                : make_float4(accp[0][xp].x, accp[1][xp].x, accp[2][xp].x, accp[3][xp].x));
+  }
+}
+
 #define UPB_STAMP(ID)                                                                      \
   do {                                                                                     \
     if (a.stamps != nullptr && blockIdx.x == 0 && threadIdx.x == 0 && first_item) a.stamps[ID] = clock64(); \
@@ -1688,48 +1735,24 @@ __device__ void graph_body(const StepArgs& a, const BlobHeader& hd, const GraphD
     const float4 bsum = exact ? pull_backward<true>(g, q, ce4, use_head) : pull_backward<false>(g, q, ce4, use_head);
     block_sum_q4(bsum, sRed, sV + V_TMP16);     // barriers inside: GPQ complete, EPQ dead
     UPB_STAMP(15+(1-l)*3);
-    if (tid < 16) gacc(gp, (l == 0 ? P_GCN0_B : P_GCN1_B) + tid, sV[V_TMP16 + tid]);
-    if (warp < KW) {   // g_W[o][c] = sum_i GPQ[i][o] h^l[i][c]: 4x4 register tiles, K split over KW warps
-      float* redbuf = smem + S_EPQ;              // [KW][512]
-      const int to = lane >> 2, tc = lane & 3;
-      // packed FMAs: accp[c][xp] = (acc[2 xp][c], acc[2 xp + 1][c]); the GPQ float4 supplies the pairs (x, y), (z, w)
-      // as they sit in registers, the h components are duplicated into both halves (FFMA2: two FMAs per issue)
-      float2 accp[4][2];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) { accp[c][0] = make_float2(0.f, 0.f); accp[c][1] = make_float2(0.f, 0.f); }
-      for (int i = warp; i < n; i += 8 * KW) {   // eight nodes per trip: their global h rows are in flight together
-        float4 gq[8], hv[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int ii = i + u * KW;
-          hv[u] = ii < n ? __ldcg(reinterpret_cast<const float4*>(hin + (size_t)ii * 16 + tc * 4)) : f4(0.f);
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int ii = i + u * KW;
-          gq[u] = ii < n ? ld4(g.GPQ + ii * 32 + to * 4) : f4(0.f);
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const float2 g01 = make_float2(gq[u].x, gq[u].y), g23 = make_float2(gq[u].z, gq[u].w);
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const float hc_ = comp(hv[u], c);
-            const float2 h2 = make_float2(hc_, hc_);
-            accp[c][0] = __ffma2_rn(g01, h2, accp[c][0]);
-            accp[c][1] = __ffma2_rn(g23, h2, accp[c][1]);
-          }
-        }
-      }
-#pragma unroll
-      for (int x = 0; x < 4; ++x) {
-        const int xp = x >> 1;
-        st4(redbuf + warp * 512 + (to * 4 + x) * 16 + tc * 4,
-            (x & 1) ? make_float4(accp[0][xp].y, accp[1][xp].y, accp[2][xp].y, accp[3][xp].y)
-                    : make_float4(accp[0][xp].x, accp[1][xp].x, accp[2][xp].x, accp[3][xp].x));
+    // layer input h^l back from the global scratch into the dead EPQ region, behind the reduction buffer: one bulk
+    // copy, in flight while the tensor-core g_h phase runs, so g_W's K loop reads h rows at shared-memory latency
+    bool hin_smem = false;
+    if constexpr (!BIG) {
+      hin_smem = n <= HIN_NODES;
+      if (hin_smem && tid == 0) {
+        fence_proxy_async();
+        mbar_expect_tx(mbar + 3, (unsigned)n * 64u);
+        bulk_g2s(smem + S_EPQ + KW * 512, hin, (unsigned)n * 64u, mbar + 3);
       }
     }
+    if (tid < 16) gacc(gp, (l == 0 ? P_GCN0_B : P_GCN1_B) + tid, sV[V_TMP16 + tid]);
     gh_phase_tc(g, Wpq, l == 1);     // g_h = g_h' + GPQ Wpq (residual), in place
+    if (hin_smem) mbar_wait(mbar + 3, l == 1 ? 0u : 1u);     // two phases per graph: parity 0 then 1
+    if (warp < KW) {   // g_W[o][c] = sum_i GPQ[i][o] h^l[i][c]: 4x4 register tiles, K split over KW warps
+      if (hin_smem) gw_partial<true>(g, smem + S_EPQ + KW * 512, n, smem + S_EPQ);
+      else gw_partial<false>(g, hin, n, smem + S_EPQ);
+    }
     __syncthreads();
     if (tid < 512) {
       const float* redbuf = smem + S_EPQ;
@@ -2139,7 +2162,7 @@ __device__ void fused_tail(const StepArgs& a, float* smem, unsigned stage_bits) 
 template <bool TRAIN>
 __global__ void __launch_bounds__(NT, 1) k_sgnn(const __grid_constant__ StepArgs a) {
   extern __shared__ __align__(16) float smem[];
-  __shared__ __align__(8) uint64_t s_mbar[3];   // bulk-copy completion: [0] graph staging, [1] EPQ reload, [2] feature reload
+  __shared__ __align__(8) uint64_t s_mbar[4];   // bulk-copy completion: [0] graph staging, [1] EPQ reload, [2] feature reload, [3] h rows for g_W
   const long long t_cta0 = a.stamps ? clock64() : 0;
   if (a.stamps && threadIdx.x == 0 && blockIdx.x == 0) {      // clock64 vs globaltimer (ns): the SM clock actually running
     unsigned long long gt;
@@ -2147,7 +2170,7 @@ __global__ void __launch_bounds__(NT, 1) k_sgnn(const __grid_constant__ StepArgs
     a.stamps[30] = t_cta0; a.stamps[32] = (long long)gt;
   }
   if (threadIdx.x == 0) {
-    mbar_init(s_mbar + 0, 1); mbar_init(s_mbar + 1, 1); mbar_init(s_mbar + 2, 1);
+    mbar_init(s_mbar + 0, 1); mbar_init(s_mbar + 1, 1); mbar_init(s_mbar + 2, 1); mbar_init(s_mbar + 3, 1);
     fence_mbar_init();
   }
   unsigned nstaged = 0;                         // graphs staged by bulk copies so far: phase parity of the mbarriers
