@@ -110,14 +110,15 @@ constexpr int S_VEC = S_WEND;
 constexpr int S_RED = S_VEC + V_END;             // [NW][20] block-reduce scratch
 constexpr int S_INV = S_RED + NW * 20;           // [NS]
 constexpr int S_ALPHA = S_INV + NS;              // [NS]
-constexpr int S_Z = S_ALPHA + NS;                // [KS]
+constexpr int S_RP = S_ALPHA + NS;               // [(NS+8)/2] u16 pairs: CSR row pointers (live to the end: g_h reads degrees)
+// from here to S_EPQ everything is dead after the last pull; the encoder backward's node features land here early
+constexpr int S_Z = S_RP + (NS + 8) / 2;         // [KS]
 constexpr int S_GZ = S_Z + KS;                   // [KS]
 constexpr int S_GHEAD = S_GZ + KS;               // [KS][16]
 constexpr int S_CUV = S_GHEAD + KS * 16;         // [KS] u32
 constexpr int S_CIDX = S_CUV + KS;               // [KS] i32
-constexpr int S_RP = S_CIDX + KS;                // [(NS+8)/2] u16 pairs
 constexpr int ORD_ROUNDS = ((NS + 7) / 8 + NW - 1) / NW + 1;   // pull-schedule rounds kept in shared memory
-constexpr int S_ORD = S_RP + (NS + 8) / 2;       // [ORD_ROUNDS][NW][8] u16: pull schedule (blob.h)
+constexpr int S_ORD = S_CIDX + KS;               // [ORD_ROUNDS][NW][8] u16: pull schedule (blob.h)
 constexpr int S_ADJ = S_ORD + ORD_ROUNDS * NW * 4;   // [AS] u32
 constexpr int S_EPQ = S_ADJ + AS;                // [NS][32]
 constexpr int S_GPQ = S_EPQ + NS * 32;           // [NS][32]   (aliased by the head-backward chunk buffers)
@@ -126,6 +127,8 @@ constexpr int S_TOTAL = S_H + NS * 16;
 constexpr size_t SMEM_BYTES = (size_t)S_TOTAL * 4;
 static_assert(SMEM_BYTES <= 232448, "shared memory budget (227 KB)");
 constexpr int KW = 16;            // warps that share the K dimension of the g_W tile reduction
+constexpr int XEARLY_NODES = (S_EPQ - S_Z) / FS;        // feature rows that fit in the candidate + CSR + adjacency stretch
+static_assert(S_Z % 4 == 0 && S_EPQ % 4 == 0, "bulk copies need 16-byte aligned shared addresses");
 constexpr int HIN_NODES = (NS * 32 - KW * 512) / 16;   // h rows that fit behind the g_W reduction buffer in the EPQ region
 static_assert(KW * 512 <= NS * 32 && NW * 384 <= NS * 32, "cross-warp reduction buffers alias the EPQ region");
 static_assert(NW == kPullWarps, "the packer lays the pull schedule out for NT / 32 warps");
@@ -1182,10 +1185,11 @@ __device__ __forceinline__ void softmax_seeds(const StepArgs& a, const BlobHeade
     }
     if (lane == 0) {
       sc[SC_GV] = 2.f * a.c_value * dv * a.inv_batch;
-      float* st = stats;
-      st[0] += dv * dv; st[1] += surr; st[2] += negent; st[3] += 1.f; st[4] += in_ind;
-      st[5] += g.stage == 0 ? 1.f : 0.f; st[6] += g.stage == 1 ? 1.f : 0.f;
-      st[7] += (isfinite(V) && isfinite(logp) && isfinite(H)) ? 0.f : 1.f;
+      // fire-and-forget adds (gacc): a read-modify-write would park this warp on an L2 round trip before the
+      // logit-gradient loop below; same thread, same addresses, so the summation order is still fixed
+      gacc(stats, 0, dv * dv); gacc(stats, 1, surr); gacc(stats, 2, negent); gacc(stats, 3, 1.f); gacc(stats, 4, in_ind);
+      gacc(stats, 5, g.stage == 0 ? 1.f : 0.f); gacc(stats, 6, g.stage == 1 ? 1.f : 0.f);
+      gacc(stats, 7, (isfinite(V) && isfinite(logp) && isfinite(H)) ? 0.f : 1.f);
     }
     // logits gradient: g_z = g_lp (delta_a - p) - g_H p (logp + H)
     for (int j = lane; j < k; j += 32) {
@@ -1740,10 +1744,18 @@ __device__ void graph_body(const StepArgs& a, const BlobHeader& hd, const GraphD
     bool hin_smem = false;
     if constexpr (!BIG) {
       hin_smem = n <= HIN_NODES;
-      if (hin_smem && tid == 0) {
+      if (tid == 0) {
         fence_proxy_async();
-        mbar_expect_tx(mbar + 3, (unsigned)n * 64u);
-        bulk_g2s(smem + S_EPQ + KW * 512, hin, (unsigned)n * 64u, mbar + 3);
+        if (hin_smem) {
+          mbar_expect_tx(mbar + 3, (unsigned)n * 64u);
+          bulk_g2s(smem + S_EPQ + KW * 512, hin, (unsigned)n * 64u, mbar + 3);
+        }
+        // after the last pull the candidate / pull-schedule / adjacency lists are dead: the node features the encoder backward
+        // needs come back into that stretch now, two phases ahead of their use
+        if (l == 0 && n <= XEARLY_NODES) {
+          mbar_expect_tx(mbar + 2, (unsigned)n * (FS * 4u));
+          bulk_g2s(smem + S_Z, g.x, (unsigned)n * (FS * 4u), mbar + 2);
+        }
       }
     }
     if (tid < 16) gacc(gp, (l == 0 ? P_GCN0_B : P_GCN1_B) + tid, sV[V_TMP16 + tid]);
@@ -1771,13 +1783,17 @@ __device__ void graph_body(const StepArgs& a, const BlobHeader& hd, const GraphD
   {
     float* redbuf = smem + S_GPQ;                // [NW][384]  (GPQ is dead after the last g_h)
     const float* xsrc = g.x;
-    if constexpr (!BIG) {                        // features back into the (dead) EPQ region, one bulk copy
-      if (tid == 0) {
-        fence_proxy_async();
-        mbar_expect_tx(mbar + 2, (unsigned)n * (FS * 4u));
-        bulk_g2s(smem + S_EPQ, g.x, (unsigned)n * (FS * 4u), mbar + 2);
+    if constexpr (!BIG) {                        // features: already on their way into the dead list stretch (above), or,
+      if (n <= XEARLY_NODES) {                   // for graphs too large for it, into the dead EPQ region now
+        xsrc = smem + S_Z;
+      } else {
+        if (tid == 0) {
+          fence_proxy_async();
+          mbar_expect_tx(mbar + 2, (unsigned)n * (FS * 4u));
+          bulk_g2s(smem + S_EPQ, g.x, (unsigned)n * (FS * 4u), mbar + 2);
+        }
+        xsrc = smem + S_EPQ;
       }
-      xsrc = smem + S_EPQ;
     }
     float4 hs = f4(0.f);
     for (int task = tid; task < n * 4; task += NT) hs = hs + ld4(g.H + (task >> 2) * 16 + q * 4);
@@ -2192,7 +2208,7 @@ __global__ void __launch_bounds__(NT, 1) k_sgnn(const __grid_constant__ StepArgs
     stage_bits |= 1u << (d.stage & 1);
     if (d.n > a.n_cap || d.e > a.e_cap || d.n < 1) {   // larger than the context was sized for: skip, flag
       if (threadIdx.x == 0) {
-        if constexpr (TRAIN) gp[G_STATS + 7] += 1.f;
+        if constexpr (TRAIN) gacc(gp, G_STATS + 7, 1.f);
         if (a.out_value) a.out_value[gid] = CUDART_NAN_F;
         if (a.out_logp) a.out_logp[gid] = CUDART_NAN_F;
         if (a.out_entropy) a.out_entropy[gid] = CUDART_NAN_F;

@@ -6,3 +6,4 @@ timeout 300 python bench.py --steps 200 --warmup 10 --skip-cpu --skip-e2e --iter
 python -c "
 import json; d=json.load(open('gpurun_out/quick_bench.json')); print(round(d['value']), d['ms_per_step'], d['roofline']['kernel_ms'], d['roofline']['frac'])"
 python tools/phase_times.py 2>&1 | grep -E "cycles|total"
+timeout 600 compute-sanitizer --tool racecheck python -m pytest tests/test_gpu_parity.py -m gpu -q -k "gradient_and_steps and hlg" 2>&1 | grep -E "RACECHECK SUMMARY|Race reported|passed|failed" | head -8
