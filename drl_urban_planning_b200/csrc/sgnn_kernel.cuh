@@ -1199,6 +1199,40 @@ __device__ __forceinline__ void softmax_seeds(const StepArgs& a, const BlobHeade
   }
 }
 
+// pull the NEXT graph of this CTA into L2 while the current one is processed (its first touches are then L2 hits):
+// feature rows, adjacency, row pointers, pull schedule, and the sample's small rows (numerical / current-node features,
+// action, return, ...).  Out of line: once per graph, and its address arithmetic stays out of the graph body's
+// register allocation.
+template <bool TRAIN>
+__device__ __noinline__ void prefetch_next_graph(const StepArgs& a, int nitem) {
+  const int T0 = threadIdx.x, TN = NT;
+  const BlobHeader& hd = *reinterpret_cast<const BlobHeader*>(a.blob);
+  const GraphDesc* descs = reinterpret_cast<const GraphDesc*>(a.blob + hd.off_desc);
+  const int ng = a.ids ? a.ids[nitem] : nitem;
+  const GraphDesc& nd = descs[ng];
+  const char* px = reinterpret_cast<const char*>(a.blob + hd.off_x) + (size_t)nd.x_row * FS * 4;
+  const char* pa = reinterpret_cast<const char*>(a.blob + hd.off_adj) + (size_t)nd.adj_off * 4;
+  const char* pr = reinterpret_cast<const char*>(a.blob + hd.off_rowptr) + (size_t)nd.rp_off * 2;
+  const char* po = reinterpret_cast<const char*>(a.blob + hd.off_order) + (size_t)nd.ord_off * 2;
+  const int bx = nd.n * FS * 4, ba = nd.e * 8, br = (nd.n + 1) * 2, bo = nd.ord_rounds * NW * 16;
+  for (int o = T0 * 128; o < bx; o += TN * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(px + o));
+  for (int o = T0 * 128; o < ba; o += TN * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pa + o));
+  for (int o = T0 * 128; o < br; o += TN * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pr + o));
+  for (int o = T0 * 128; o < bo; o += TN * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(po + o));
+  if (T0 >= TN - 32) {
+    const int w = T0 - (TN - 32);
+    const void* q = nullptr;
+    if (w < 3) q = reinterpret_cast<const char*>(a.blob + hd.off_num) + (size_t)ng * NUMD * 4 + min(w * 128, NUMD * 4 - 4);
+    else if (w < 5) q = reinterpret_cast<const char*>(a.blob + hd.off_cur) + (size_t)ng * FS * 4 + (w - 3) * (FS * 4 - 4);
+    else if (w == 5) q = a.actions ? a.actions + (size_t)ng * 2 : nullptr;
+    else if (TRAIN && w == 6) q = a.ret + ng;
+    else if (TRAIN && w == 7) q = a.exps + ng;
+    else if (TRAIN && w == 8) q = a.fixed_lp + ng;
+    else if (TRAIN && w == 9) q = a.adv + ng;
+    if (q) asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
+  }
+}
+
 // partial g_W tile of one warp: redbuf[warp][o][c] = sum over this warp's nodes of GPQ[i][o] h[i][c]; 4x4 register
 // tiles (lane = 8 output groups x 4 channel groups), eight nodes per trip.  SMEM: h rows staged in shared memory,
 // else read from the global scratch (L2).
@@ -1329,18 +1363,23 @@ __device__ void graph_body(const StepArgs& a, const BlobHeader& hd, const GraphD
     g.ord = reinterpret_cast<const uint16_t*>(smem + S_ORD);
   }
   float* vn = smem + S_GPQ;          // value-head / numeric-encoder weights live in the idle GPQ region
+  // per-graph vectors and scalars (numerical features, current-node features, action / return / ... of this sample):
+  // one word per thread, LOADED before the weight staging and stored after it, so this round trip (DRAM-cold for the
+  // per-sample arrays) overlaps the staging's instead of following it -- the slowest warp sets the barrier below
+  const float* psrc = nullptr;
+  float* pdst = nullptr;
+  if (tid < NUMD) { psrc = gnum + tid; pdst = sV + V_X52 + tid; }
+  else if (tid >= 64 && tid < 64 + FS) { psrc = gcur + (tid - 64); pdst = sV + V_XCUR + (tid - 64); }
+  else if (tid >= 96 && tid < 109) pdst = sc + (tid - 96);                             // zeroed scalar slots
+  else if (tid == 109) { if (a.actions) { psrc = a.actions + ((size_t)gid * 2 + g.stage); pdst = sc + SC_ACT; } }
+  else if (tid == 114) pdst = sc + SC_QUEUE;                                           // candidate queue head = 0
+  else if (TRAIN && tid == 110) { psrc = a.ret + gid; pdst = sc + SC_RET; }            // consumed by the softmax warp
+  else if (TRAIN && tid == 111) { psrc = a.exps + gid; pdst = sc + SC_EXP; }
+  else if (TRAIN && tid == 112) { psrc = a.fixed_lp + gid; pdst = sc + SC_FLP; }
+  else if (TRAIN && tid == 113) { psrc = a.adv + gid; pdst = sc + SC_ADV; }
+  const float pval = psrc ? __ldg(psrc) : 0.f;
   stage_vn_weights(P, vn);
-  if (tid < NUMD) sV[V_X52 + tid] = gnum[tid];
-  if (tid >= 64 && tid < 64 + FS) sV[V_XCUR + tid - 64] = gcur[tid - 64];
-  if (tid >= 96 && tid < 109) sc[tid - 96] = 0.f;
-  if (tid == 109 && a.actions) sc[SC_ACT] = a.actions[(size_t)gid * 2 + g.stage];     // per-graph scalars: fetched early,
-  if constexpr (TRAIN) {                                                             // consumed by the softmax warp
-    if (tid == 110) sc[SC_RET] = a.ret[gid];
-    if (tid == 111) sc[SC_EXP] = a.exps[gid];
-    if (tid == 112) sc[SC_FLP] = a.fixed_lp[gid];
-    if (tid == 113) sc[SC_ADV] = a.adv[gid];
-  }
-  if (tid == 114) reinterpret_cast<int*>(sc)[SC_QUEUE] = 0;
+  if (pdst) *pdst = pval;
   if constexpr (!BIG) mbar_wait(mbar, mpar);
   __syncthreads();
   UPB_STAMP(1);
@@ -2215,21 +2254,7 @@ __global__ void __launch_bounds__(NT, 1) k_sgnn(const __grid_constant__ StepArgs
       }
       continue;
     }
-    {   // pull the NEXT graph of this CTA into L2 while this one is processed (its first touches are then L2 hits)
-      const int nitem = item + gridDim.x;
-      if (nitem < a.count) {
-        const GraphDesc& nd = descs[a.ids ? a.ids[nitem] : nitem];
-        const char* px = reinterpret_cast<const char*>(a.blob + hd.off_x) + (size_t)nd.x_row * FS * 4;
-        const char* pa = reinterpret_cast<const char*>(a.blob + hd.off_adj) + (size_t)nd.adj_off * 4;
-        const char* pr = reinterpret_cast<const char*>(a.blob + hd.off_rowptr) + (size_t)nd.rp_off * 2;
-        const char* po = reinterpret_cast<const char*>(a.blob + hd.off_order) + (size_t)nd.ord_off * 2;
-        const int bx = nd.n * FS * 4, ba = nd.e * 8, br = (nd.n + 1) * 2, bo = nd.ord_rounds * NW * 16;
-        for (int o = threadIdx.x * 128; o < bx; o += NT * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(px + o));
-        for (int o = threadIdx.x * 128; o < ba; o += NT * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pa + o));
-        for (int o = threadIdx.x * 128; o < br; o += NT * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pr + o));
-        for (int o = threadIdx.x * 128; o < bo; o += NT * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(po + o));
-      }
-    }
+    if (item + (int)gridDim.x < a.count) prefetch_next_graph<TRAIN>(a, item + gridDim.x);
     const bool big = d.n > NS || 2 * d.e > AS || d.k > KS || d.ord_rounds > ORD_ROUNDS;
     // stamps: the SECOND graph of CTA 0 (steady state)
     if (big) graph_body<TRAIN, true>(a, hd, d, gid, smem, gp, scr, item == (int)(blockIdx.x + gridDim.x), s_mbar, 0u);
