@@ -1417,7 +1417,6 @@ __device__ void graph_body(const StepArgs& a, const BlobHeader& hd, const GraphD
     for (int f = 0; f < 24; ++f) w[f] = *reinterpret_cast<const float2*>(sW + S_WET + f * 16 + c2);
     const float2 be = *reinterpret_cast<const float2*>(sW + S_BE + c2);
     const float* xs = smem + S_EPQ;
-    UPB_WSTAMP_B();
     for (int i = warp * 4 + (lane >> 3); i < n; i += NW * 4) {
       const float4* xr = reinterpret_cast<const float4*>(xs + i * FS);
       float2 acc = be;
@@ -1433,7 +1432,6 @@ __device__ void graph_body(const StepArgs& a, const BlobHeader& hd, const GraphD
       if (TRAIN) *reinterpret_cast<float2*>(g.H0g + i * 16 + c2) = acc;
     }
   }
-  UPB_WSTAMP();
   if (warp == NW - 1 && lane < 16) {   // current node through the same encoder (state_encoder.py:190-191)
     float s = sW[S_BE + lane];
 #pragma unroll
@@ -1553,6 +1551,13 @@ __device__ void graph_body(const StepArgs& a, const BlobHeader& hd, const GraphD
       if (j >= k) break;
       float t0, t1, xin;
       head_units(hl, g, j, lane, t0, t1, xin);
+      if (TRAIN && j < CH) {   // the backward pass starts from these instead of recomputing its first chunk (the buffers sit
+                               // behind the value-head weights in the GPQ region, idle until the backward pulls)
+        float* cGU = smem + S_GPQ + HB_GU;
+        cGU[j * 32 + (lane & 15)] = t0;
+        cGU[j * 32 + (lane & 15) + 16] = t1;
+        smem[S_GPQ + HB_X + j * 16 + (lane & 15)] = xin;
+      }
       const float zj = half_sum(hl.w20 * t0 + hl.w21 * t1, hl.mask);
       if ((lane & 15) == 0) g.z[j] = zj;
     }
@@ -1589,22 +1594,35 @@ __device__ void graph_body(const StepArgs& a, const BlobHeader& hd, const GraphD
     do {
       const int cn = min(CH, k - base);
       {
-        HeadLane hl;
-        head_lane_init(hl, g, sW, sV, lane);
-        const int hw = warp * 2 + (lane >> 4);
+        const int hw = warp * 2 + (lane >> 4), c16 = lane & 15;
         float a00 = 0.f, a01 = 0.f, a10 = 0.f, a11 = 0.f;
-        for (int jj = hw; jj < cn; jj += 2 * NW) {
-          float t0, t1, xin;
-          head_units(hl, g, base + jj, lane, t0, t1, xin);
-          const float gzj = g.gz[base + jj];
-          const float gu0 = gzj * hl.w20 * (1.f - t0 * t0), gu1 = gzj * hl.w21 * (1.f - t1 * t1);
-          cGU[jj * 32 + (lane & 15)] = gu0;
-          cGU[jj * 32 + (lane & 15) + 16] = gu1;
-          cX[jj * 16 + (lane & 15)] = xin;
-          a00 += gu0; a01 += gu1; a10 = fmaf(gzj, t0, a10); a11 = fmaf(gzj, t1, a11);
+        if (base == 0) {   // first chunk: hidden activations t and head inputs were left in cGU / cX by the forward pass
+          const float* w2 = g.stage == 0 ? sW + S_LUW1 : sW + S_RDW1;
+          const float w20 = w2[c16], w21 = w2[c16 + 16];
+          for (int jj = hw; jj < cn; jj += 2 * NW) {
+            const float t0 = cGU[jj * 32 + c16], t1 = cGU[jj * 32 + c16 + 16];
+            const float gzj = g.gz[jj];
+            const float gu0 = gzj * w20 * (1.f - t0 * t0), gu1 = gzj * w21 * (1.f - t1 * t1);
+            cGU[jj * 32 + c16] = gu0;
+            cGU[jj * 32 + c16 + 16] = gu1;
+            a00 += gu0; a01 += gu1; a10 = fmaf(gzj, t0, a10); a11 = fmaf(gzj, t1, a11);
+          }
+        } else {           // later chunks: recompute the candidates' hidden units
+          HeadLane hl;
+          head_lane_init(hl, g, sW, sV, lane);
+          for (int jj = hw; jj < cn; jj += 2 * NW) {
+            float t0, t1, xin;
+            head_units(hl, g, base + jj, lane, t0, t1, xin);
+            const float gzj = g.gz[base + jj];
+            const float gu0 = gzj * hl.w20 * (1.f - t0 * t0), gu1 = gzj * hl.w21 * (1.f - t1 * t1);
+            cGU[jj * 32 + c16] = gu0;
+            cGU[jj * 32 + c16 + 16] = gu1;
+            cX[jj * 16 + c16] = xin;
+            a00 += gu0; a01 += gu1; a10 = fmaf(gzj, t0, a10); a11 = fmaf(gzj, t1, a11);
+          }
         }
-        pGC[hw * 32 + (lane & 15)] = a00; pGC[hw * 32 + (lane & 15) + 16] = a01;
-        pGW2[hw * 32 + (lane & 15)] = a10; pGW2[hw * 32 + (lane & 15) + 16] = a11;
+        pGC[hw * 32 + c16] = a00; pGC[hw * 32 + c16 + 16] = a01;
+        pGW2[hw * 32 + c16] = a10; pGW2[hw * 32 + c16 + 16] = a11;
       }
       __syncthreads();
       UPB_STAMP(12);

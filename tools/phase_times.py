@@ -39,6 +39,7 @@ for i in [1, 2, 3, 4, 5, 6, 7, 8, 9, 20, 10, 11, 12, 14, 15, 16, 17, 18, 19, 21]
 print("total", tot, "cycles")
 if st[46:62].any():
     print("warp probe (cycles after stamp 1):", [int(x - st[1]) for x in st[46:62]])
+print("stamps rel. to stamp 1:", {i: int(st[i] - st[1]) for i in range(2, 22) if st[i]})
 if st[212:224].any():
     print("warp probe B, warps 0-11 (cycles after stamp 1):", [int(x - st[1]) for x in st[212:224]])
 busy = st[64:64 + eng.grid]; pro = st[224:224 + eng.grid]

@@ -1,2 +1,2 @@
 #!/bin/bash
-python tools/phase_times.py 2>&1 | grep -E "probe|h0"
+python tools/phase_times.py 2>&1 | grep -E "probe|stamps rel"

@@ -12,3 +12,5 @@ run
 for v in variants/*.so; do [ -f "$v" ] || continue; echo "== $v"; export UPB_LIB=$PWD/$v
 timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q 2>&1 | tail -1
 run; done
+unset UPB_LIB
+timeout 600 compute-sanitizer --tool racecheck python -m pytest tests/test_gpu_parity.py -m gpu -q -k "gradient_and_steps and (hlg or small)" 2>&1 | grep -E "RACECHECK SUMMARY|Race reported|passed|failed" | head -8
