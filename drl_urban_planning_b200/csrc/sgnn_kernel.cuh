@@ -1660,7 +1660,55 @@ __device__ void graph_body(const StepArgs& a, const BlobHeader& hd, const GraphD
     if (tid < 32) sV[V_GC + tid] = gcr;
     if (tid >= 32 && tid < 64) sV[V_GW2 + tid - 32] = gw2r;
   }
+  // ---- attention backward.  g_v' = Wo^T g_att and g_hbar = Vc^T g_v' per warp in registers (lane & 15 = component).
+  // Runs BEFORE the barrier that closes the head backward: it needs nothing from it (value-path gradients, alpha and
+  // h^L only; every head-backward read of h^L lies before that loop's last internal barrier), so its dependent chains
+  // and the node loop overlap the other warps' last head-backward chunk instead of following the barrier.
+  float gvp_c, ghbar_c;
+  float4 gsh = f4(0.f);
+  {
+    const int c = lane & 15;
+    const float gatt = sV[V_GSV + 48 + c];
+    float s = 0.f;
+#pragma unroll
+    for (int r = 0; r < 16; ++r) s = fmaf(sW[S_WO + r * 16 + c], __shfl_sync(0xffffffffu, gatt, r), s);
+    gvp_c = s;
+    s = 0.f;
+#pragma unroll
+    for (int r = 0; r < 16; ++r) s = fmaf(sW[S_VC + r * 16 + c], __shfl_sync(0xffffffffu, gvp_c, r), s);
+    ghbar_c = s;
+    if (warp == 0 && lane < 16) {
+      sV[V_GVP + c] = gvp_c;
+      sV[V_CE + c] = e > 0 ? sV[V_GSV + 32 + c] / (float)e : 0.f;
+    }
+  }
+  {
+    float gdot = ghbar_c * sV[V_HBAR + (lane & 15)];
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) gdot += __shfl_xor_sync(0xffffffffu, gdot, o);     // sum over the 16 components
+    const float4 gh4 = make_float4(__shfl_sync(0xffffffffu, ghbar_c, q * 4), __shfl_sync(0xffffffffu, ghbar_c, q * 4 + 1),
+                                   __shfl_sync(0xffffffffu, ghbar_c, q * 4 + 2), __shfl_sync(0xffffffffu, ghbar_c, q * 4 + 3));
+    const float4 qk4 = make_float4(__shfl_sync(0xffffffffu, qk_c, q * 4), __shfl_sync(0xffffffffu, qk_c, q * 4 + 1),
+                                   __shfl_sync(0xffffffffu, qk_c, q * 4 + 2), __shfl_sync(0xffffffffu, qk_c, q * 4 + 3));
+    const float4 gmn4 = ld4(sV + V_GSV + 16 + q * 4) * (1.f / (float)n);
+    const float invZ = 1.f / sc[SC_Z];
+    for (int task = tid; task < ((n * 4 + 31) & ~31); task += NT) {
+      const int i = task >> 2;
+      const float4 h = i < n ? ld4(g.H + i * 16 + q * 4) : f4(0.f);
+      float dp = dot4(gh4, h);
+      dp += __shfl_xor_sync(0xffffffffu, dp, 1);
+      dp += __shfl_xor_sync(0xffffffffu, dp, 2);
+      if (i < n) {
+        const float ai = g.alpha[i] * invZ;
+        const float gs = ai * (dp - gdot);
+        gsh = gsh + h * gs;
+        // g_h^L = g_mean/n + a_i g_hbar (value path) + g_s qk (key path); stored scaled by 1/(deg+eps), over h^L
+        st4(g.H + i * 16 + q * 4, (gmn4 + gh4 * ai + qk4 * gs) * g.inv[i]);
+      }
+    }
+  }
   __syncthreads();
+  UPB_STAMP(13);
   if (g.stage == 0) {
     if (tid < 512) {
       const int r_ = tid >> 4, c_ = tid & 15;
@@ -1690,51 +1738,7 @@ __device__ void graph_body(const StepArgs& a, const BlobHeader& hd, const GraphD
     if (tid < 32) { gacc(gp, P_RD_B0 + tid, sV[V_GC + tid]); gacc(gp, P_RD_W1 + tid, sV[V_GW2 + tid]); }
   }
 
-  // ---- attention backward.  g_v' = Wo^T g_att and g_hbar = Vc^T g_v' per warp in registers (lane & 15 = component).
-  float gvp_c, ghbar_c;
-  {
-    const int c = lane & 15;
-    const float gatt = sV[V_GSV + 48 + c];
-    float s = 0.f;
-#pragma unroll
-    for (int r = 0; r < 16; ++r) s = fmaf(sW[S_WO + r * 16 + c], __shfl_sync(0xffffffffu, gatt, r), s);
-    gvp_c = s;
-    s = 0.f;
-#pragma unroll
-    for (int r = 0; r < 16; ++r) s = fmaf(sW[S_VC + r * 16 + c], __shfl_sync(0xffffffffu, gvp_c, r), s);
-    ghbar_c = s;
-    if (warp == 0 && lane < 16) {
-      sV[V_GVP + c] = gvp_c;
-      sV[V_CE + c] = e > 0 ? sV[V_GSV + 32 + c] / (float)e : 0.f;
-    }
-  }
-  {
-    float gdot = ghbar_c * sV[V_HBAR + (lane & 15)];
-#pragma unroll
-    for (int o = 8; o > 0; o >>= 1) gdot += __shfl_xor_sync(0xffffffffu, gdot, o);     // sum over the 16 components
-    const float4 gh4 = make_float4(__shfl_sync(0xffffffffu, ghbar_c, q * 4), __shfl_sync(0xffffffffu, ghbar_c, q * 4 + 1),
-                                   __shfl_sync(0xffffffffu, ghbar_c, q * 4 + 2), __shfl_sync(0xffffffffu, ghbar_c, q * 4 + 3));
-    const float4 qk4 = make_float4(__shfl_sync(0xffffffffu, qk_c, q * 4), __shfl_sync(0xffffffffu, qk_c, q * 4 + 1),
-                                   __shfl_sync(0xffffffffu, qk_c, q * 4 + 2), __shfl_sync(0xffffffffu, qk_c, q * 4 + 3));
-    const float4 gmn4 = ld4(sV + V_GSV + 16 + q * 4) * (1.f / (float)n);
-    const float invZ = 1.f / sc[SC_Z];
-    float4 gsh = f4(0.f);
-    for (int task = tid; task < ((n * 4 + 31) & ~31); task += NT) {
-      const int i = task >> 2;
-      const float4 h = i < n ? ld4(g.H + i * 16 + q * 4) : f4(0.f);
-      float dp = dot4(gh4, h);
-      dp += __shfl_xor_sync(0xffffffffu, dp, 1);
-      dp += __shfl_xor_sync(0xffffffffu, dp, 2);
-      if (i < n) {
-        const float ai = g.alpha[i] * invZ;
-        const float gs = ai * (dp - gdot);
-        gsh = gsh + h * gs;
-        // g_h^L = g_mean/n + a_i g_hbar (value path) + g_s qk (key path); stored scaled by 1/(deg+eps), over h^L
-        st4(g.H + i * 16 + q * 4, (gmn4 + gh4 * ai + qk4 * gs) * g.inv[i]);
-      }
-    }
-    block_sum_q4(gsh, sRed, sV + V_GSH);
-  }
+  block_sum_q4(gsh, sRed, sV + V_GSH);
   if (warp == 0) {   // g_q' = Kc gsh / 4, g_hc += Qc^T g_q', composed-projection gradients
     const int c = lane & 15;
     float s = 0.f;

@@ -9,7 +9,7 @@ from drl_urban_planning_b200.packing import pack_states
 
 NAMES = {1: "setup (lists, VN weights)", 2: "h0 + hc + numeric L0", 3: "epq L0 (+num L1, Weff)", 4: "pull fwd L0", 5: "epq L1",
          6: "pull fwd L1 + means", 7: "attention fwd", 8: "  warp 0: value tail done", 9: "value head || policy head (barrier)", 20: "  warp 0: softmax done", 11: "  warp 0: value/num bwd done", 10: "softmax + seeds + g_z",
-         12: "head bwd A || value/num bwd", 14: "head bwd B/C + attention bwd", 15: "pull bwd L1", 16: "gW/g_h L1",
+         12: "head bwd A || value/num bwd", 13: "head bwd B/C", 14: "head grads + attention bwd", 15: "pull bwd L1", 16: "gW/g_h L1",
          17: "epq L0 (recompute)", 18: "pull bwd L0", 19: "gW/g_h L0", 21: "node encoder bwd"}
 dev = torch.device("cuda", 0)
 count = int(sys.argv[1]) if len(sys.argv) > 1 else 256
@@ -32,7 +32,7 @@ torch.cuda.synchronize()
 st = stamps.cpu().numpy()
 print("graph 0: n, e, k, stage =", blob.info[0])
 prev, tot = st[0], st[21] - st[0]
-for i in [1, 2, 3, 4, 5, 6, 7, 8, 9, 20, 10, 11, 12, 14, 15, 16, 17, 18, 19, 21]:
+for i in [1, 2, 3, 4, 5, 6, 7, 8, 9, 20, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 21]:
     if st[i] == 0: continue
     print(f"{i:3d} {NAMES.get(i, ''):28s} {st[i] - prev:8d} cycles  {100.0 * (st[i] - prev) / tot:5.1f}%")
     prev = st[i]
