@@ -23,7 +23,7 @@ extern "C" {
 
 #define UPB_ABI_VERSION 1
 
-/* model dimensions: fixed by every shipped config (cfg/exp_cfg/.../*.yaml state_encoder_specs,
+/* model dimensions: fixed by every shipped config (the yaml files under cfg/exp_cfg: state_encoder_specs,
  * policy_specs, value_specs); other shapes are rejected by the host layer. */
 #define UPB_NODE_DIM 23
 #define UPB_NODE_STRIDE 24      /* node-feature rows are stored padded to 24 floats (16-byte aligned rows) */
